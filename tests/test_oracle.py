@@ -1,0 +1,106 @@
+"""CPU tests that pin the oracle (oracle/zel_oracle.c) to the reference.
+
+The reference repository has no tests or golden vectors of its own, so
+the pins are: the PCG64 known answers recorded in SURVEY.md §4, the golden ic_* records
+in tests/golden/ produced by the unmodified reference sources (make_golden.py), and —
+when oracle/_ref/zeldovich_ref is present — a live run of that binary.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+
+M = 65536
+
+
+def test_pcg64_known_answers(oracle):
+    d = oracle.pcg_draws(12346, 0, 4)
+    assert list(d) == [13376226141762278320, 13264298068723250620, 14189328008317063736, 6008591607947420752]
+    assert oracle.pcg_draws(12346, 2 * M * M, 1)[0] == 14931042480954944222
+    assert oracle.pcg_draws(12346, 2 * (3 * M * M + (M - 5) * M + 7), 1)[0] == 7757910958070640359
+
+
+def test_pcg64_matches_numpy(oracle):
+    # numpy's PCG64 is the same setseq_xsl_rr_128_64 generator; inject the seeded state
+    mult = (2549297995355413924 << 64) | 4865540595714422341
+    inc = (6364136223846793005 << 64) | 1442695040888963407
+    mask = (1 << 128) - 1
+    for seed in (0, 1, 12346, (1 << 64) - 7):
+        bg = np.random.PCG64(0)
+        st = bg.state
+        st["state"] = {"state": ((seed + inc) * mult + inc) & mask, "inc": inc}
+        bg.state = st
+        bg.advance(123456789012345)
+        want = bg.random_raw(16)
+        got = oracle.pcg_draws(seed, 123456789012345, 16)
+        assert np.array_equal(want, got)
+
+
+def test_one_rand_range(oracle):
+    assert oracle.one_rand((1 << 64) - 1) == 1.0
+    assert oracle.one_rand(0) == 2.0**-64
+    assert oracle.one_rand((1 << 63) - 1) == 0.5
+    assert oracle.one_rand((1 << 64) - 2) == 1.0  # rounds to nearest even
+
+
+def test_normalisation_scalar(oracle):
+    cfg = oracle.make_config(64)
+    s = oracle.power_scalars(cfg, helpers.wmap_pk())
+    # sigma(8) after normalisation must come back as ZD_Pk_sigma
+    assert abs(s["sigma_check"] - 0.0210839935761) < 1e-12
+    # reference prints "Input sigma(8.000000) = 0.0781753" (golden stderr)
+    sig_in = 0.0210839935761 / np.sqrt(s["normalization"] * 720.0**3)
+    assert abs(sig_in - 0.0781753) < 5e-8
+
+
+@pytest.mark.parametrize("name", sorted(helpers.golden_cases().keys()))
+def test_oracle_matches_golden(oracle, name):
+    case, raw, eig, _ = helpers.load_golden(name)
+    kw = helpers.params_to_kwargs(case["params"])
+    cfg = oracle.make_config(**kw)
+    rec, st = oracle.run(cfg, helpers.wmap_pk(), eig)
+    gold = raw.view(oracle.RECORD_DTYPES[cfg.icformat])
+    if "ijk" in gold.dtype.names:
+        assert np.array_equal(rec["ijk"], gold["ijk"])
+    for f in ("displ", "vel"):
+        if f in gold.dtype.names:
+            for c in range(3):
+                err = oracle.field_rel_err(rec[f][:, c], gold[f][:, c])
+                tol = 1e-6 if gold[f].dtype == np.float32 else 1e-12
+                assert err < tol, (name, f, c, err)
+    N = cfg.ppd
+    assert abs(np.sqrt(st["density_variance"] / N**3) - case["stderr"]["rms_density"]) < 1e-6
+    assert np.allclose(st["max_disp"], case["stderr"]["max_disp"], rtol=2e-6)
+
+
+def test_oracle_oversampling_identity(oracle):
+    # PPD=2N with k_cutoff=2, sampled at even sites, equals PPD=N
+    pk = helpers.wmap_pk()
+    a, _ = oracle.run(oracle.make_config(16, icformat="Zeldovich"), pk)
+    b, _ = oracle.run(oracle.make_config(32, k_cutoff=2.0, icformat="Zeldovich"), pk)
+    b = b.reshape(32, 32, 32)[::2, ::2, ::2].reshape(-1)
+    for c in range(3):
+        assert oracle.field_rel_err(b["displ"][:, c], a["displ"][:, c]) < 1e-13
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(helpers.ROOT, "oracle", "_ref", "zeldovich_ref")), reason="reference binary not built")
+def test_oracle_matches_live_reference(oracle):
+    synth = helpers.load_synth()
+    k, p = helpers.wmap_pk()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_power_table(os.path.join(tmp, "pk.pow"), k, p)
+        synth.write_eigmodes(os.path.join(tmp, "eig.bin"), 16)
+        over = dict(NP=32**3, ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="3.0", ICFormat='"RVdoubleZel"',
+                    ZD_Pk_filename='"pk.pow"', ZD_PLT_filename='"eig.bin"', ZD_Seed=99, ZD_k_cutoff="1.0")
+        synth.write_param(os.path.join(tmp, "c.par"), **over)
+        oracle.run_reference("c.par", cwd=tmp, threads=4)
+        ref = oracle.read_ic_dir(os.path.join(tmp, "ic_out"), 32, 375, "RVdoubleZel")
+    cfg = oracle.make_config(32, seed=99, qPLT=1, qPLTrescale=1, PLT_target_z=3.0, icformat="RVdoubleZel")
+    rec, _ = oracle.run(cfg, (k, p), (16, synth.make_eigmodes(16)))
+    assert np.array_equal(rec["ijk"], ref["ijk"])
+    for f in ("displ", "vel"):
+        for c in range(3):
+            assert oracle.field_rel_err(rec[f][:, c], ref[f][:, c]) < 1e-12
