@@ -1,0 +1,203 @@
+/* zeldovich_b200.h — C ABI of the B200-native zeldovich-PLT initial-conditions hot path.
+ *
+ * The reference (abacusorg/zeldovich-PLT) is a single C++ executable with no FFI; the
+ * seam this library replaces is the numerical body of its main():
+ *
+ *     Setup_FFTW(ppd, ...)                      reference src/zeldovich.cpp:938  (:41-75)
+ *     BlockArray array(ppd, numblock, narray…)  reference src/zeldovich.cpp:962-970
+ *     ZeldovichZ(array, param, Pk, 0, NULL)     reference src/zeldovich.cpp:971  (:517-601, LoadPlane :278-515)
+ *     ZeldovichXY(array, param)                 reference src/zeldovich.cpp:982  (:611-695)
+ *       -> WriteParticlesSlab(...)              reference src/output.cpp:41-234
+ *     globals eig_vecs / density_variance / max_disp
+ *
+ * Everything crossing this boundary is a plain pointer, size or POD struct.  All
+ * functions return 0 on success or a ZPLT_E* code; zplt_last_error() gives the text.
+ * No C++ exception crosses the boundary.  A context is not re-entrant; use one host
+ * thread per context (one context per GPU).
+ *
+ * There is NO CPU fallback: every compute entry point fails with ZPLT_ECUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef ZELDOVICH_B200_H
+#define ZELDOVICH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZPLT_OK 0
+#define ZPLT_EINVAL 1   /* bad argument / unsupported configuration */
+#define ZPLT_ECUDA 2    /* CUDA runtime failure (including: no device) */
+#define ZPLT_ESTATE 3   /* call made in the wrong order */
+#define ZPLT_ENOMEM 4
+
+/* ICFormat record layouts, same order as the reference's OutputType enum
+ * (reference include/output.h:19-49). */
+#define ZPLT_FMT_ZELDOVICH 0   /* u16 i,j,k; pad; double displ[3]              32 B */
+#define ZPLT_FMT_RVZEL 1       /* u16 i,j,k; pad; float displ[3]; float vel[3] 32 B */
+#define ZPLT_FMT_RVDOUBLEZEL 2 /* u16 i,j,k; pad; double displ[3], vel[3]      56 B */
+#define ZPLT_FMT_ZELSIMPLE 3   /* float displ[3]                               12 B */
+
+/* What the kernels need from reference class Parameters (include/parameters.h:14-74)
+ * after Parameters::setup() (src/parameters.cpp:97-197). */
+typedef struct zplt_config {
+    int64_t ppd;          /* particles per dimension; power of two, 16..4096 */
+    double boxsize;       /* BoxSize */
+    int64_t seed;         /* ZD_Seed as the reference widens it: (int) sign-extended (src/power_spectrum.cpp:14) */
+    double k_cutoff;      /* ZD_k_cutoff >= 1 */
+    int32_t corner_modes; /* ZD_CornerModes */
+    int32_t qonemode;     /* ZD_qonemode */
+    int32_t one_mode[3];  /* ZD_one_mode */
+    int32_t qPLT;         /* ZD_qPLT: 4 packed arrays instead of 2 */
+    int32_t qPLTrescale;  /* ZD_qPLT_rescale */
+    int32_t fixed_power;  /* ZD_qPk_fix_to_mean */
+    double PLT_target_z;  /* ZD_PLT_target_z */
+    double z_initial;     /* InitialRedshift */
+    double f_cluster;     /* ZD_f_cluster */
+    int32_t icformat;     /* ZPLT_FMT_* */
+    int32_t device;       /* CUDA device ordinal, or -1 for the current device */
+    int32_t rank;         /* slab decomposition: this context's rank ... */
+    int32_t nranks;       /* ... of nranks (1 = whole problem on this GPU) */
+} zplt_config;
+
+typedef struct zplt_ctx zplt_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int zplt_create(const zplt_config *cfg, zplt_ctx **out);
+void zplt_destroy(zplt_ctx *ctx);
+const char *zplt_last_error(void);
+/* bytes of one record of the configured ICFormat (reference sizeof_outputtype, src/output.cpp:254-280) */
+size_t zplt_record_bytes(int32_t icformat);
+/* number of packed complex arrays: 4 with qPLT, else 2 (reference src/zeldovich.cpp:871-876) */
+int zplt_narray(const zplt_ctx *ctx);
+
+/* ---- inputs (host pointers; copied) ------------------------------------------- */
+/* Spline of ln P against ln k as reference SplineFunction holds it after spline()
+ * (include/spline_function.h:105-139): n sorted nodes x, values y, second derivatives
+ * y2; plus PowerSpectrum::normalization and Pk_smooth2 after Normalize()
+ * (src/power_spectrum.cpp:186-223).  Replaces the per-mode PowerSpectrum::power call
+ * (src/power_spectrum.cpp:225-261). */
+int zplt_set_power_spline(zplt_ctx *ctx, int32_t n, const double *x, const double *y, const double *y2,
+                          double normalization, double Pk_smooth2);
+/* Power-law branch of PowerSpectrum::power (src/power_spectrum.cpp:233-236). */
+int zplt_set_power_law(zplt_ctx *ctx, double index, double normalization, double Pk_smooth2);
+/* PLT eigenmode table exactly as load_eigmodes reads it (src/zeldovich.cpp:794-830):
+ * double[ppd_e][ppd_e][ppd_e/2+1][4].  Required when qPLT != 0. */
+int zplt_set_eigenmodes(zplt_ctx *ctx, int32_t ppd_e, const double *table);
+
+/* ---- device resources ---------------------------------------------------------- */
+/* Bytes of device workspace the context needs (spectral slabs + tables). */
+size_t zplt_workspace_bytes(const zplt_ctx *ctx);
+/* Optional: hand the context a caller-owned device buffer (e.g. a torch tensor's
+ * data_ptr) of at least zplt_workspace_bytes(); otherwise it cudaMallocs its own. */
+int zplt_set_workspace(zplt_ctx *ctx, void *device_ptr, size_t bytes);
+/* Optional: run on a caller-owned cudaStream_t (passed as void*); default is a private stream. */
+int zplt_set_stream(zplt_ctx *ctx, void *cuda_stream);
+
+/* ---- the hot path -------------------------------------------------------------- */
+/* Stage 1+2 of the reference (ZeldovichZ + the y half of ZeldovichXY's 2-D FFT): draw
+ * the modes, build the packed spectral arrays, inverse-FFT along z and y.  Leaves the
+ * arrays resident in HBM, x axis still in Fourier space.  Asynchronous on the stream. */
+int zplt_generate(zplt_ctx *ctx);
+/* Stage 3 (x half of Inverse2dFFT + WriteParticlesSlab): inverse-FFT along x and emit
+ * the records of planes z0 .. z0+nz-1 in (z, y, x) order into `device_out`
+ * (nz*ppd*ppd*record_bytes bytes of device memory, or pinned host memory mapped into
+ * the device address space).  Accumulates density_variance and max_disp.  Asynchronous. */
+int zplt_emit_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *device_out);
+/* Convenience for host callers: emit planes z0..z0+nz-1 and copy them to `host_out`
+ * (pageable or pinned), double-buffered through an internal staging ring.  Synchronous. */
+int zplt_fetch_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *host_out);
+/* Reset the statistics accumulated by the emit calls. */
+int zplt_reset_stats(zplt_ctx *ctx);
+/* density_variance = sum over emitted particles of dens^2; max_disp[j] = signed value of
+ * the largest |pos[j]| (reference globals, src/output.cpp:28-30,190-197).  Synchronises. */
+int zplt_get_stats(zplt_ctx *ctx, double *density_variance, double max_disp[3]);
+/* Block until everything queued on the context's stream has finished. */
+int zplt_synchronize(zplt_ctx *ctx);
+/* Milliseconds the device spent in each stage of the last generate/emit calls
+ * (CUDA events on the context's stream): out[0]=mode generation, out[1]=z FFT,
+ * out[2]=y FFT, out[3]=x FFT + emission (summed over emit calls since the last generate).
+ * Also out[4..7] = number of kernel launches in each of those stages. */
+int zplt_get_timings(zplt_ctx *ctx, double out[8]);
+
+/* ---- introspection for parity tests (small sizes; host output buffers) --------- */
+/* n raw pcg64 outputs starting (off_hi*2^64+off_lo) draws after seeding with `seed`,
+ * computed on the device with the same jump-table composition the mode kernel uses. */
+int zplt_dbg_pcg_draws(uint64_t seed, uint64_t off_hi, uint64_t off_lo, int64_t n, uint64_t *host_out);
+/* For n modes given as signed integer wavevectors k[3*i..3*i+2] (ky in [0,ppd/2)): the
+ * two raw draws each mode consumes (raw[2*i], raw[2*i+1]) and their (0,1] images. */
+int zplt_dbg_mode_draws(zplt_ctx *ctx, int64_t n, const int32_t *k, uint64_t *host_raw, double *host_u);
+/* P(k) at k = sqrt(m)*fundamental for m = 0..count-1, as the mode kernel sees it. */
+int zplt_dbg_power_table(zplt_ctx *ctx, int64_t count, double *host_out);
+/* The packed spectral arrays [narray][z][y][x] (complex double) before any FFT. */
+int zplt_dbg_spectral(zplt_ctx *ctx, double *host_out);
+/* The arrays after zplt_generate (z and y transformed, x not yet). */
+int zplt_dbg_after_generate(zplt_ctx *ctx, double *host_out);
+/* Unnormalised backward 1-D FFTs of length n on host data laid out [batch][n]
+ * (row_mode=1, contiguous pencils) or [n][batch] (row_mode=0, strided pencils), in place. */
+int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *host_data);
+
+
+/* ==== host side of the boundary (C++ implementation, no device work) ================
+ * Mirrors of reference class Parameters / PowerSpectrum / load_eigmodes / the ic_* file
+ * writer, exported with C linkage so that tests and bindings can check the host scalars
+ * and drive a whole run. */
+
+/* Parameters after parsing + setup() (reference include/parameters.h:14-74). */
+typedef struct zplt_params {
+    double boxsize, Pk_scale, separation, fundamental, nyquist, k_cutoff;
+    double Pk_norm, Pk_sigma, Pk_sigma_ratio, f_cluster, Pk_smooth, Pk_powerlaw_index;
+    double z_initial, PLT_target_z, f_NL, n_s, Omega_M;
+    int64_t ppd, np;
+    int32_t cpd, numblock, qdensity, qascii, qoneslab, seed, qPk_fix_to_mean, qonemode, one_mode[3];
+    int32_t qPLT, qPLTrescale, AllowDirectIO, version, CornerModes;
+    char Pk_filename[1024], output_dir[1024], density_filename[1024], PLT_filename[1024], ICFormat[64];
+} zplt_params;
+
+/* Parse a ParseHeader-style parameter file and run the reference's validity checks
+ * (reference src/parameters.cpp:11-197).  ZPLT_EINVAL + message on any failure. */
+int zplt_params_load(const char *param_file, zplt_params *out);
+/* ICFormat string -> ZPLT_FMT_* (reference src/output.cpp:256-279), -1 if unknown. */
+int zplt_icformat_code(const char *icformat);
+/* Fill a zplt_config from parsed parameters (device = -1, rank 0 of 1). */
+int zplt_config_from_params(const zplt_params *p, zplt_config *out);
+
+/* Host PowerSpectrum: InitFromFile / InitFromPowerLaw + Normalize
+ * (reference src/power_spectrum.cpp:130-223). */
+typedef struct zplt_power zplt_power;
+int zplt_power_create(const zplt_params *p, zplt_power **out);
+void zplt_power_destroy(zplt_power *pk);
+int zplt_power_info(const zplt_power *pk, int32_t *n_nodes, double *normalization, double *Pk_smooth2);
+int zplt_power_arrays(const zplt_power *pk, double *x, double *y, double *y2);
+double zplt_power_eval(zplt_power *pk, double wavenumber);  /* PowerSpectrum::power */
+double zplt_power_sigmaR(zplt_power *pk, double R);         /* PowerSpectrum::sigmaR */
+/* Hand the spline (or power law) to a device context: calls zplt_set_power_spline/_law. */
+int zplt_power_apply(zplt_power *pk, zplt_ctx *ctx);
+
+/* load_eigmodes (reference src/zeldovich.cpp:794-830): read `int32 ppd_e` + table, check the
+ * file size, and pass it to zplt_set_eigenmodes. */
+int zplt_load_eigenmodes_file(zplt_ctx *ctx, const char *path);
+
+/* SetupOutputDir + the ZeldovichXY write loop (reference src/output.cpp:236-251, :208-212;
+ * src/zeldovich.cpp:667-682): remove stale ic_* / zeldovich.* files, then append plane z to
+ * `output_dir/ic_{z*cpd/ppd}` in ascending z.  Needs zplt_generate to have run. */
+int zplt_write_ic_files(zplt_ctx *ctx, const char *output_dir, int32_t cpd);
+
+/* What `zeldovich <param_file>` does end to end (reference main, src/zeldovich.cpp:848-1032);
+ * the report carries the numbers the reference prints on stderr. */
+typedef struct zplt_run_report {
+    double density_variance, rms_density, max_disp[3];
+    double input_sigma, sigma_prediction;
+    double seconds_total, seconds_preamble, seconds_device, seconds_write;
+    double stage_ms[4];
+    int64_t ppd, files_written, bytes_written;
+} zplt_run_report;
+int zplt_run_param_file(const char *param_file, int32_t device, int32_t write_files, zplt_run_report *report);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZELDOVICH_B200_H */

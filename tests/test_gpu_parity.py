@@ -1,0 +1,283 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+golden fixtures produced by the unmodified reference.
+
+Bars (BASELINE.json north_star): RNG draws, mode ordering and particle ids bit-exact;
+displacements and velocities within 1e-10, defined field-relative (max|a-b|/max|b| per
+component); float32 ICFormats are compared after the cast and must agree
+to one float ulp of the field scale (2e-7) — in practice they are almost always bit-equal.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+from __graft_entry__ import load_package, load_synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+M = 65536
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+def make_ctx(pkg, kw, pk, eig):
+    """Product context from keyword parameters; the spline comes from the product's own host code."""
+    synth = load_synth()
+    tmp = tempfile.mkdtemp(prefix="zplt_")
+    synth.write_power_table(os.path.join(tmp, "pk.pow"), pk[0], pk[1])
+    fmtname = kw["icformat"]
+    over = dict(NP=kw["ppd"] ** 3, BoxSize=repr(float(kw["boxsize"])), ZD_Seed=kw["seed"], ZD_k_cutoff=repr(float(kw["k_cutoff"])),
+                ZD_CornerModes=kw.get("corner_modes", 0), ZD_qPLT=kw["qPLT"], ZD_qPLT_rescale=kw["qPLTrescale"],
+                ZD_PLT_target_z=repr(float(kw["PLT_target_z"])), InitialRedshift=repr(float(kw["z_initial"])),
+                ZD_f_cluster=repr(float(kw["f_cluster"])), ZD_qPk_fix_to_mean=kw["fixed_power"],
+                ZD_Pk_norm=repr(float(kw["Pk_norm"])), ZD_Pk_smooth=repr(float(kw["Pk_smooth"])),
+                ZD_Pk_scale=repr(float(kw["Pk_scale"])), ICFormat='"%s"' % fmtname,
+                ZD_Pk_filename='"%s"' % os.path.join(tmp, "pk.pow"))
+    if kw["Pk_sigma"] > 0:
+        over["ZD_Pk_sigma"] = repr(float(kw["Pk_sigma"]))
+    else:
+        over["ZD_Pk_sigma"] = 0
+        over["ZD_Pk_sigma_ratio"] = repr(float(kw["Pk_sigma_ratio"]))
+    if eig is not None:
+        synth_path = os.path.join(tmp, "eig.bin")
+        with open(synth_path, "wb") as f:
+            f.write(np.int32(eig[0]).tobytes())
+            f.write(np.ascontiguousarray(eig[1], dtype=np.float64).tobytes())
+        over["ZD_PLT_filename"] = '"%s"' % synth_path
+    synth.write_param(os.path.join(tmp, "c.par"), **over)
+    P = pkg.Parameters(os.path.join(tmp, "c.par"))
+    power = pkg.PowerSpectrum(P)
+    ctx = pkg.Context(P.config(device=0))
+    power.apply(ctx)
+    if eig is not None:
+        ctx.load_eigenmodes_file(P.PLT_filename)
+    return ctx, P, power
+
+
+def default_kw(**over):
+    kw = dict(ppd=32, boxsize=720.0, seed=12346, k_cutoff=1.0, corner_modes=0, qPLT=0, qPLTrescale=0, PLT_target_z=0.0,
+              z_initial=49.0, f_cluster=1.0, fixed_power=0, Pk_norm=8.0, Pk_sigma=0.0210839935761, Pk_sigma_ratio=0.0,
+              Pk_smooth=0.0, Pk_scale=1.0, icformat="RVZel")
+    kw.update(over)
+    return kw
+
+
+def compare_records(oracle, got, want, tol64=TOL, tol32=2e-7):
+    if "ijk" in want.dtype.names:
+        assert np.array_equal(got["ijk"], want["ijk"]), "particle ids differ"
+        assert np.all(got["pad"] == 0)
+    worst = 0.0
+    for f in ("displ", "vel"):
+        if f in want.dtype.names:
+            tol = tol32 if want[f].dtype == np.float32 else tol64
+            for c in range(3):
+                err = oracle.field_rel_err(got[f][:, c], want[f][:, c])
+                assert err < tol, (f, c, err)
+                worst = max(worst, err)
+    return worst
+
+
+# ---------------------------------------------------------------- RNG ---------------
+def test_pcg64_device_known_answers(pkg):
+    d = pkg.pcg_draws(12346, 0, 4)
+    assert list(d) == [13376226141762278320, 13264298068723250620, 14189328008317063736, 6008591607947420752]
+    assert pkg.pcg_draws(12346, 2 * M * M, 1)[0] == 14931042480954944222
+    assert pkg.pcg_draws(12346, 2 * (3 * M * M + (M - 5) * M + 7), 1)[0] == 7757910958070640359
+
+
+def test_pcg64_device_vs_oracle(pkg, oracle):
+    for seed, off in ((0, 0), (12346, 123456789012345), (-7, (1 << 70) + 12345), ((1 << 63) + 5, 2 * 511 * M * M + 17)):
+        assert np.array_equal(pkg.pcg_draws(seed, off, 64), oracle.pcg_draws(seed, off, 64))
+
+
+@pytest.mark.parametrize("ppd", [16, 64, 256])
+def test_mode_draws_bit_exact(pkg, oracle, ppd):
+    """Closed-form RNG position of every mode == the reference's sequential nskip walk (via the oracle)."""
+    ctx, P, power = make_ctx(pkg, default_kw(ppd=ppd), helpers.wmap_pk(), None)
+    rng = np.random.RandomState(1)
+    h = ppd // 2
+    k = np.stack([rng.randint(-h + 1, h + 1, 4000), rng.randint(0, h, 4000), rng.randint(-h + 1, h + 1, 4000)], axis=1)
+    k[:8] = [[0, 0, 0], [h, 0, 0], [-h + 1, h - 1, -h + 1], [h, h - 1, h], [-1, 0, -1], [1, 1, 1], [0, h - 1, 0], [-1, 3, h]]
+    raw, u = ctx.mode_draws(k)
+    for i in range(len(k)):
+        kx, ky, kz = (int(v) for v in k[i])
+        off = 2 * (ky * M * M + (kz % M) * M + (kx % M))
+        want = oracle.pcg_draws(12346, off, 2)
+        assert raw[i, 0] == want[0] and raw[i, 1] == want[1], (k[i], raw[i], want)
+        assert u[i, 0] == oracle.one_rand(want[0]) and u[i, 1] == oracle.one_rand(want[1])
+    ctx.close()
+
+
+# ---------------------------------------------------------------- host boundary -----
+def test_host_scalars_match_oracle(pkg, oracle):
+    kw = default_kw(ppd=64)
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), None)
+    s = oracle.power_scalars(oracle.make_config(**kw), helpers.wmap_pk())
+    assert abs(power.normalization / s["normalization"] - 1) < 1e-14
+    assert P.fundamental == 2.0 * np.pi / 720.0
+    n = 3 * 32 * 32 + 1
+    got = ctx.power_table(n)
+    want = oracle.power_table(oracle.make_config(**kw), helpers.wmap_pk(), n)
+    assert got[0] == 0.0
+    assert np.max(np.abs(got[1:] / want[1:] - 1)) < 1e-13
+    ctx.close()
+
+
+# ---------------------------------------------------------------- FFT ---------------
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("row_mode", [True, False])
+def test_fft_matches_numpy(pkg, n, row_mode):
+    rng = np.random.RandomState(n)
+    batch = 64
+    shape = (batch, n) if row_mode else (n, batch)
+    a = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    got = pkg.fft_backward(a, row_mode)
+    want = np.fft.ifft(a, axis=1 if row_mode else 0) * n  # unnormalised backward, sign +1
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-14
+
+
+def test_fft_linearity_and_impulse(pkg):
+    n, batch = 1024, 32
+    a = np.zeros((batch, n), dtype=np.complex128)
+    for b in range(batch):
+        a[b, (7 * b + 1) % n] = 1.0
+    got = pkg.fft_backward(a, True)
+    j = np.arange(n)
+    for b in range(batch):
+        want = np.exp(2j * np.pi * j * ((7 * b + 1) % n) / n)
+        assert np.max(np.abs(got[b] - want)) < 1e-13
+
+
+# ---------------------------------------------------------------- spectral arrays ---
+@pytest.mark.parametrize("case", [
+    dict(ppd=32),
+    dict(ppd=32, k_cutoff=2.0, corner_modes=1),
+    dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, f_cluster=0.97, icformat="RVdoubleZel", eig=16),
+    dict(ppd=32, qPLT=1, icformat="RVZel", eig=64),
+    dict(ppd=32, fixed_power=1, seed=-3),
+])
+def test_spectral_arrays_before_fft(pkg, oracle, case):
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    got = ctx.spectral()
+    want = oracle.spectral_cube(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got - want)) / scale < 1e-13
+    # masked sites are exactly zero in both
+    assert np.array_equal(got == 0, want == 0)
+    ctx.close()
+
+
+# ---------------------------------------------------------------- full path ---------
+@pytest.mark.parametrize("name", sorted(helpers.golden_cases().keys()))
+def test_full_path_matches_golden(pkg, oracle, name):
+    """CUDA path vs ic_* records written by the unmodified reference."""
+    case, raw, eig, _ = helpers.load_golden(name)
+    kw = default_kw(**helpers.params_to_kwargs(case["params"]))
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    ctx.generate()
+    got = ctx.fetch_planes(0, kw["ppd"])
+    gold = raw.view(ctx.record_dtype)
+    compare_records(oracle, got, gold, tol64=1e-10)
+    st = ctx.stats()
+    N = kw["ppd"]
+    assert abs(np.sqrt(st["density_variance"] / N**3) - case["stderr"]["rms_density"]) < 1e-6
+    assert np.allclose(st["max_disp"], case["stderr"]["max_disp"], rtol=2e-6)
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", [
+    dict(ppd=64, icformat="RVZel"),
+    dict(ppd=128, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=128),
+    dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=128),
+    dict(ppd=128, k_cutoff=2.0, icformat="Zeldovich"),
+    dict(ppd=64, icformat="ZelSimple", boxsize=250.0, seed=77),
+])
+def test_full_path_matches_oracle(pkg, oracle, case):
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    ctx.generate()
+    got = ctx.fetch_planes(0, kw["ppd"])
+    want, wst = oracle.run(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    worst = compare_records(oracle, got, want)
+    st = ctx.stats()
+    assert abs(st["density_variance"] / wst["density_variance"] - 1) < 1e-10
+    assert np.allclose(st["max_disp"], wst["max_disp"], rtol=1e-10)
+    print(case, "worst field-relative error", worst)
+    ctx.close()
+
+
+def test_oversampled_pair_phase_matched(pkg, oracle):
+    """BASELINE config 3: PPD=N and PPD=2N with ZD_k_cutoff=2 carry the same modes."""
+    pk = helpers.wmap_pk()
+    recs = {}
+    for ppd, kc in ((64, 1.0), (128, 2.0)):
+        ctx, P, power = make_ctx(pkg, default_kw(ppd=ppd, k_cutoff=kc, icformat="Zeldovich"), pk, None)
+        ctx.generate()
+        recs[ppd] = ctx.fetch_planes(0, ppd)
+        ctx.close()
+    b = recs[128].reshape(128, 128, 128)[::2, ::2, ::2].reshape(-1)
+    for c in range(3):
+        assert oracle.field_rel_err(b["displ"][:, c], recs[64]["displ"][:, c]) < 1e-12
+
+
+def test_plane_ranges_and_file_writer(pkg, oracle):
+    kw = default_kw(ppd=32, icformat="RVZel")
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), None)
+    ctx.generate()
+    whole = ctx.fetch_planes(0, 32)
+    part = ctx.fetch_planes(5, 9)
+    assert np.array_equal(part.view(np.uint8), whole.reshape(32, -1)[5:14].reshape(-1).view(np.uint8))
+    with tempfile.TemporaryDirectory() as tmp:
+        ctx.write_ic_files(tmp, 5)  # cpd < ppd: several planes share a file, ascending-z append order
+        rec = oracle.read_ic_dir(tmp, 32, 5, "RVZel")
+        assert np.array_equal(rec.view(np.uint8), whole.view(np.uint8))
+        assert sorted(os.listdir(tmp)) == sorted({"ic_%d" % (z * 5 // 32) for z in range(32)})
+    ctx.close()
+
+
+def test_cli_matches_reference_layout(pkg, oracle):
+    """./zeldovich <param_file> writes the same files the reference writes (golden case)."""
+    import subprocess
+
+    case, raw, eig, text = helpers.load_golden("plt16_interp_rvdouble")
+    synth = load_synth()
+    k, p = helpers.wmap_pk()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_power_table(os.path.join(tmp, "pk.pow"), k, p)
+        with open(os.path.join(tmp, "eig.bin"), "wb") as f:
+            f.write(np.int32(eig[0]).tobytes())
+            f.write(np.ascontiguousarray(eig[1]).tobytes())
+        with open(os.path.join(tmp, "case.par"), "w") as f:
+            f.write(text)
+        r = subprocess.run([pkg.CLI_PATH, "case.par"], cwd=tmp, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        rec = oracle.read_ic_dir(os.path.join(tmp, "ic_out"), 16, int(case["params"]["CPD"]), "RVdoubleZel")
+        gold = raw.view(rec.dtype)
+        compare_records(oracle, rec, gold)
+        assert "rms density variation of the pixels is 0.007389" in r.stderr
+    r = subprocess.run([pkg.CLI_PATH], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
+
+
+def test_errors_are_reported(pkg):
+    with pytest.raises(pkg.ZpltError):
+        pkg.Context(pkg.make_config(48))  # not a power of two
+    ctx = pkg.Context(pkg.make_config(32))
+    with pytest.raises(pkg.ZpltError):
+        ctx.generate()  # power spectrum not set
+    ctx.close()

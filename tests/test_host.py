@@ -1,0 +1,157 @@
+"""CPU tests of the host side of the boundary: the C-ABI library loads and exports every
+declared symbol, the ParseHeader-compatible reader, Parameters checks, and the host
+PowerSpectrum (spline + sigma(R) normalisation) against the oracle.  No device calls."""
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+from __graft_entry__ import ROOT, load_package, load_synth
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = load_package()
+    p.lib()
+    return p
+
+
+def write_case(tmp, pk=None, **over):
+    synth = load_synth()
+    k, p = pk if pk is not None else helpers.wmap_pk()
+    synth.write_power_table(os.path.join(tmp, "pk.pow"), k, p)
+    over.setdefault("ZD_Pk_filename", '"%s"' % os.path.join(tmp, "pk.pow"))
+    return synth.write_param(os.path.join(tmp, "c.par"), **over)
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "zeldovich_b200.h")).read()
+    declared = set(re.findall(r"\b(zplt_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg.EXPORTS), declared ^ set(pkg.EXPORTS)
+    L = pkg.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_struct_layouts_match_header(pkg):
+    # sizes the C compiler produced for the same declarations
+    import ctypes as C
+    import subprocess
+
+    src = '#include "zeldovich_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n",sizeof(zplt_config),sizeof(zplt_params),sizeof(zplt_run_report));return 0;}\n'
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "s.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(tmp, "s.c"), "-o", os.path.join(tmp, "s")])
+        out = subprocess.check_output([os.path.join(tmp, "s")], text=True).split()
+    assert [int(v) for v in out] == [C.sizeof(pkg.Config), C.sizeof(pkg.Params), C.sizeof(pkg.RunReport)]
+
+
+def test_no_device_means_error_not_fallback(pkg):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.ZpltError) as e:
+        pkg.Context(pkg.make_config(32))
+    assert e.value.code == pkg.ECUDA
+
+
+def test_parameters_example_values(pkg):
+    with tempfile.TemporaryDirectory() as tmp:
+        path = write_case(tmp, NP=64**3)
+        P = pkg.Parameters(path)
+    assert P.ppd == 64 and P.np == 262144 and P.cpd == 375 and P.numblock == 4
+    assert P.boxsize == 720.0 and P.seed == 12346 and P.version == 2
+    assert P.ICFormat == "RVZel" and P.output_dir == "./ic_out"
+    assert P.separation == 720.0 / 64 and P.fundamental == 2.0 * np.pi / 720.0 and P.nyquist == np.pi / (720.0 / 64)
+    # the reference scanner's own decimal conversion: digits / 10^n, not strtod
+    assert P.Pk_sigma == 210839935761.0 / 1e13
+    assert P.qoneslab == -1 and P.f_cluster == 1.0 and P.Pk_powerlaw_index == 1000
+
+
+def test_parser_grammar(pkg):
+    text = (
+        "# leading comment\n"
+        "##\nBoxSize = 1   # inside a block comment\n##\n"
+        'BoxSize = 2.5D2   # Fortran exponent\n'
+        "CPD = 11\nNP = 4096\nZD_NumBlock = 2\nZD_Pk_scale = 1\nZD_Seed = -5\nZD_Pk_norm = 0\n"
+        "ZD_Pk_sigma = 1.0\nZD_Pk_smooth = 0\nInitialRedshift = 9\nICFormat = ZelSimple\n"
+        "InitialConditionsDirectory = 'out dir'\nZD_Version = 2.0\n"
+        "ZD_Pk_powerlaw_index = -1.5\n"
+        "ZD_one_mode = 1 \\\n   -2 3\nZD_qonemode = 1\n"
+        "SomeUnknownKey = 3 4 5\n"
+        "\x02\nBoxSize = 999\n"
+    )
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "g.par")
+        open(path, "w").write(text)
+        P = pkg.Parameters(path)
+    assert P.boxsize == 250.0 and P.seed == -5 and P.ICFormat == "ZelSimple" and P.output_dir == "out dir"
+    assert P.version == 2 and P.one_mode == [1, -2, 3] and P.Pk_powerlaw_index == -1.5 and P.ppd == 16
+
+
+@pytest.mark.parametrize("bad,msg", [
+    (dict(ZD_Version=None), "ZD_Version"),
+    (dict(NP=1000001), "perfect cube"),
+    (dict(ZD_Pk_sigma=0), "exactly one of Pk_sigma"),
+    (dict(ZD_k_cutoff="0.5"), "k_cutoff"),
+    (dict(ZD_qPLT=1), "ZD_PLT_filename"),
+    (dict(ZD_NumBlock=3), "NumBlock"),
+    (dict(ZD_f_cluster="1.5"), "f_cluster"),
+    (dict(ZD_Pk_powerlaw_index="-1"), "exactly one of ZD_Pk_filename"),
+])
+def test_parameter_checks(pkg, bad, msg):
+    with tempfile.TemporaryDirectory() as tmp:
+        over = dict(bad)
+        drop = [k for k, v in over.items() if v is None]
+        path = write_case(tmp, **{k: v for k, v in over.items() if v is not None})
+        if drop:
+            lines = [l for l in open(path) if not any(l.startswith(k + " ") for k in drop)]
+            open(path, "w").writelines(lines)
+        with pytest.raises(pkg.ZpltError) as e:
+            pkg.Parameters(path)
+    assert msg in str(e.value)
+
+
+def test_host_power_spectrum_matches_oracle(pkg, oracle):
+    with tempfile.TemporaryDirectory() as tmp:
+        P = pkg.Parameters(write_case(tmp, NP=64**3))
+        pk = pkg.PowerSpectrum(P)
+        s = oracle.power_scalars(oracle.make_config(64), helpers.wmap_pk())
+        assert abs(pk.normalization / s["normalization"] - 1) < 1e-14
+        assert pk.n == 176
+        # sigma(8) comes back as ZD_Pk_sigma; the unnormalised value is what the reference prints
+        assert abs(pk.sigmaR(8.0) - 0.0210839935761 / 720.0**1.5) < 1e-15
+        want = oracle.power_table(oracle.make_config(64), helpers.wmap_pk(), 200)
+        fund = 2 * np.pi / 720.0
+        got = np.array([pk.power(np.sqrt(m * fund * fund)) for m in range(200)])
+        assert got[0] == 0 and np.max(np.abs(got[1:] / want[1:] - 1)) < 1e-14
+        x, y, y2 = pk.arrays()
+        assert np.all(np.diff(x) > 0) and y2[0] == 0 and y2[-1] == 0
+
+
+def test_host_power_law_and_sigma_ratio(pkg, oracle):
+    with tempfile.TemporaryDirectory() as tmp:
+        path = write_case(tmp, NP=32**3, ZD_Pk_filename='""', ZD_Pk_powerlaw_index="-2.0", ZD_Pk_sigma=0, ZD_Pk_sigma_ratio="0.5",
+                          ZD_Pk_smooth="1.5")
+        P = pkg.Parameters(path)
+        pk = pkg.PowerSpectrum(P)
+    cfg = oracle.make_config(32, is_powerlaw=1, powerlaw_index=-2.0, Pk_sigma=0.0, Pk_sigma_ratio=0.5, Pk_smooth=1.5)
+    s = oracle.power_scalars(cfg, None)
+    assert pk.normalization == s["normalization"] and pk.Pk_smooth2 == 2.25 and pk.n == 0
+    want = oracle.power_table(cfg, None, 50)
+    fund = 2 * np.pi / 720.0
+    got = np.array([pk.power(np.sqrt(m * fund * fund)) for m in range(50)])
+    assert np.max(np.abs(got[1:] / want[1:] - 1)) < 1e-14
+
+
+def test_cli_usage_and_bad_file(pkg):
+    import subprocess
+
+    r = subprocess.run([pkg.CLI_PATH], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
+    r = subprocess.run([pkg.CLI_PATH, "/nonexistent.par"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1

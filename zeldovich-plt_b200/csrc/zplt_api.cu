@@ -1,0 +1,610 @@
+// C ABI of libzeldovich_b200 (see include/zeldovich_b200.h): context management, host
+// side table construction, kernel sequencing.  No CPU compute fallback exists here: every
+// entry point that needs the device fails with ZPLT_ECUDA when CUDA is unusable.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/zeldovich_b200.h"
+#include "zplt_internal.h"
+
+using namespace zplt;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (cudaError_t) (call);                                                        \
+        if (_e != cudaSuccess) return fail(ZPLT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---------------------------------------------------------------- host tables -----
+namespace zplt {
+u128 pcg_seed_state(uint64_t seed) {
+    // engine(itype state) : state_(bump(state + increment())) — reference pcg_random.hpp:427-432
+    const u128 M = {ZPLT_PCG_MULT_LO, ZPLT_PCG_MULT_HI};
+    const u128 C = {ZPLT_PCG_INC_LO, ZPLT_PCG_INC_HI};
+    u128 s       = {seed, 0};
+    return add128(mul128(add128(s, C), M), C);
+}
+// The affine map equal to `delta` LCG steps (Brown's O(log delta) jump-ahead, the method
+// behind pcg's advance(), reference pcg_random.hpp:664-686), kept as (mult, plus) so the
+// device can compose jumps instead of looping.
+Affine pcg_jump(unsigned __int128 delta) {
+    u128 cm = {ZPLT_PCG_MULT_LO, ZPLT_PCG_MULT_HI};
+    u128 cp = {ZPLT_PCG_INC_LO, ZPLT_PCG_INC_HI};
+    Affine a;
+    a.mult = {1, 0};
+    a.plus = {0, 0};
+    const u128 one = {1, 0};
+    while (delta > 0) {
+        if (delta & 1) {
+            a.mult = mul128(a.mult, cm);
+            a.plus = add128(mul128(a.plus, cm), cp);
+        }
+        cp = mul128(add128(cm, one), cp);
+        cm = mul128(cm, cm);
+        delta >>= 1;
+    }
+    return a;
+}
+}  // namespace zplt
+
+static const long long MAXPPD = 65536;  // reference include/zeldovich.h:34
+
+// ---------------------------------------------------------------- context ---------
+#define ZPLT_MAX_EMIT_EVENTS 256
+
+struct zplt_ctx {
+    zplt_config cfg;
+    int N, na, device;
+    GenParams gp;
+    double vnorm;
+    cudaStream_t stream, copy_stream;
+    bool own_stream;
+    // device memory
+    cplx *cube;
+    bool own_cube;
+    size_t cube_bytes;
+    double *ptab;
+    long long ptab_count;
+    double *spx, *spy, *spy2;
+    u128 *ystate;
+    Affine *zjump, *xjump;
+    double *eig;
+    cplx *tw;
+    double *stats;
+    bool have_power, have_eig, generated;
+    // fetch staging
+    unsigned char *stage_dev[2];
+    size_t stage_bytes;
+    cudaEvent_t stage_free[2], stage_full[2];
+    // timing
+    cudaEvent_t ev_gen[4];
+    cudaEvent_t ev_emit[2 * ZPLT_MAX_EMIT_EVENTS];
+    int n_emit_ev;
+    int launches[4];
+};
+
+extern "C" const char *zplt_last_error(void) { return g_err.c_str(); }
+
+extern "C" size_t zplt_record_bytes(int32_t f) {
+    switch (f) {
+        case ZPLT_FMT_ZELDOVICH: return 32;
+        case ZPLT_FMT_RVZEL: return 32;
+        case ZPLT_FMT_RVDOUBLEZEL: return 56;
+        case ZPLT_FMT_ZELSIMPLE: return 12;
+    }
+    return 0;
+}
+
+extern "C" int zplt_narray(const zplt_ctx *ctx) { return ctx ? ctx->na : 0; }
+
+static int upload(void **dptr, const void *h, size_t bytes, cudaStream_t st) {
+    CK(cudaMalloc(dptr, bytes));
+    CK(cudaMemcpyAsync(*dptr, h, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
+    if (!cfg || !out) return fail(ZPLT_EINVAL, "null argument");
+    *out = nullptr;
+    const long long N = cfg->ppd;
+    if (N < 16 || N > 2048 || (N & (N - 1)))
+        return fail(ZPLT_EINVAL, "ppd=%lld unsupported: this build handles power-of-two ppd in [16, 2048]", N);
+    if (!(cfg->boxsize > 0)) return fail(ZPLT_EINVAL, "BoxSize must be positive");
+    if (!(cfg->k_cutoff >= 1)) return fail(ZPLT_EINVAL, "ZD_k_cutoff must be >= 1");
+    if (!(cfg->f_cluster > 0. && cfg->f_cluster <= 1.)) return fail(ZPLT_EINVAL, "ZD_f_cluster must be in (0,1]");
+    if (zplt_record_bytes(cfg->icformat) == 0) return fail(ZPLT_EINVAL, "unknown ICFormat code %d", cfg->icformat);
+    if (cfg->qPLT && !(cfg->icformat == ZPLT_FMT_RVZEL || cfg->icformat == ZPLT_FMT_RVDOUBLEZEL))
+        return fail(ZPLT_EINVAL, "ZD_qPLT requires an RV* ICFormat (reference src/parameters.cpp:169)");
+    if (cfg->nranks != 1 || cfg->rank != 0) return fail(ZPLT_EINVAL, "slab decomposition (nranks>1) is not built yet");
+
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(ZPLT_ECUDA, "no CUDA device");
+    int dev = cfg->device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(ZPLT_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+
+    zplt_ctx *c = new zplt_ctx();
+    memset(c, 0, sizeof(*c));
+    c->cfg    = *cfg;
+    c->N      = (int) N;
+    c->na     = cfg->qPLT ? 4 : 2;
+    c->device = dev;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev_gen[i]));
+    for (int i = 0; i < 2 * ZPLT_MAX_EMIT_EVENTS; i++) CK(cudaEventCreate(&c->ev_emit[i]));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->stage_full[i], cudaEventDisableTiming));
+    }
+    c->cube_bytes = (size_t) c->na * N * N * N * sizeof(cplx);
+
+    // derived scalars, written exactly as the reference computes them
+    GenParams &g  = c->gp;
+    g.N           = (int) N;
+    g.half        = (int) (N / 2);
+    g.na          = c->na;
+    g.corner_modes = cfg->corner_modes;
+    g.qonemode     = cfg->qonemode;
+    for (int i = 0; i < 3; i++) g.one_mode[i] = cfg->one_mode[i];
+    g.qPLT        = cfg->qPLT;
+    g.qPLTrescale = cfg->qPLTrescale;
+    g.fixed_power = cfg->fixed_power;
+    g.fundamental  = 2.0 * M_PI / cfg->boxsize;             // src/parameters.cpp:176
+    g.fundamental2 = g.fundamental * g.fundamental;         // src/zeldovich.cpp:301
+    double separation = cfg->boxsize / N;                   // src/parameters.cpp:174
+    double nyquist    = M_PI / separation;                  // src/parameters.cpp:175
+    g.k2_cutoff    = nyquist * nyquist / (cfg->k_cutoff * cfg->k_cutoff);  // src/zeldovich.cpp:318-319
+    double ik_cutoff = 1.0 / cfg->k_cutoff;                 // src/zeldovich.cpp:302
+    g.kmax         = (int) ((double) (N / 2) * ik_cutoff + .5);            // src/zeldovich.cpp:350
+    g.f_cluster    = cfg->f_cluster;
+    g.target_f     = (sqrt(1. + 24 * cfg->f_cluster) - 1) / 4.;            // src/zeldovich.cpp:305
+    double a_NL = 1.0, a0 = 1.0;
+    if (cfg->qPLTrescale) {                                  // src/zeldovich.cpp:307-312
+        a_NL = 1. / (1 + cfg->PLT_target_z);
+        a0   = 1. / (1 + cfg->z_initial);
+    }
+    g.growth_ratio = a_NL / a0;
+    c->vnorm       = cfg->qPLT ? 1.0 : (sqrt(1. + 24 * cfg->f_cluster) - 1) * .25;  // src/output.cpp:78-82
+
+    // RNG tables (reference src/power_spectrum.cpp:26-37 per-plane generators, and the
+    // nskip bookkeeping of src/zeldovich.cpp:335,341 turned into per-row/per-column jumps)
+    {
+        std::vector<u128> ys(N / 2);
+        u128 s0 = pcg_seed_state((uint64_t) cfg->seed);
+        Affine plane = pcg_jump((unsigned __int128) 2 * MAXPPD * MAXPPD);
+        ys[0]        = s0;
+        for (long long i = 1; i < N / 2; i++) ys[i] = apply(plane, ys[i - 1]);
+        std::vector<Affine> zj(N), xj(N);
+        for (long long i = 0; i < N; i++) {
+            long long k  = i > N / 2 ? i - N : i;
+            long long km = k < 0 ? k + MAXPPD : k;
+            zj[i]        = pcg_jump((unsigned __int128) 2 * MAXPPD * km);
+            xj[i]        = pcg_jump((unsigned __int128) 2 * km);
+        }
+        int rc;
+        if ((rc = upload((void **) &c->ystate, ys.data(), ys.size() * sizeof(u128), c->stream))) return rc;
+        if ((rc = upload((void **) &c->zjump, zj.data(), zj.size() * sizeof(Affine), c->stream))) return rc;
+        if ((rc = upload((void **) &c->xjump, xj.data(), xj.size() * sizeof(Affine), c->stream))) return rc;
+        g.ystate = c->ystate;
+        g.zjump  = c->zjump;
+        g.xjump  = c->xjump;
+    }
+    // twiddles W_N^j = exp(+2 pi i j / N)
+    {
+        std::vector<cplx> tw(N);
+        for (long long j = 0; j < N; j++) {
+            long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double) j / (long double) N;
+            tw[j]           = make_double2((double) cosl(ang), (double) sinl(ang));
+        }
+        int rc;
+        if ((rc = upload((void **) &c->tw, tw.data(), tw.size() * sizeof(cplx), c->stream))) return rc;
+    }
+    c->ptab_count = 3LL * (N / 2) * (N / 2) + 1;
+    CK(cudaMalloc((void **) &c->ptab, c->ptab_count * sizeof(double)));
+    g.ptab = c->ptab;
+    CK(cudaMalloc((void **) &c->stats, ZPLT_STAT_SLOTS * 8 * sizeof(double)));
+    CK(cudaMemsetAsync(c->stats, 0, ZPLT_STAT_SLOTS * 8 * sizeof(double), c->stream));
+    *out = c;
+    return ZPLT_OK;
+}
+
+extern "C" void zplt_destroy(zplt_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->own_cube && c->cube) cudaFree(c->cube);
+    cudaFree(c->ptab);
+    cudaFree(c->spx);
+    cudaFree(c->spy);
+    cudaFree(c->spy2);
+    cudaFree(c->ystate);
+    cudaFree(c->zjump);
+    cudaFree(c->xjump);
+    cudaFree(c->eig);
+    cudaFree(c->tw);
+    cudaFree(c->stats);
+    for (int i = 0; i < 2; i++) {
+        if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
+        cudaEventDestroy(c->stage_free[i]);
+        cudaEventDestroy(c->stage_full[i]);
+    }
+    for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev_gen[i]);
+    for (int i = 0; i < 2 * ZPLT_MAX_EMIT_EVENTS; i++) cudaEventDestroy(c->ev_emit[i]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+// ---------------------------------------------------------------- inputs ----------
+static int build_power_table(zplt_ctx *c, int is_powerlaw, double index, int n, double normalization, double smooth2) {
+    CK(launch_power_table(c->ptab, c->ptab_count, c->gp.fundamental2, is_powerlaw, index, n, c->spx, c->spy, c->spy2,
+                          normalization, smooth2, c->stream));
+    c->have_power = true;
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_set_power_spline(zplt_ctx *c, int32_t n, const double *x, const double *y, const double *y2,
+                                     double normalization, double Pk_smooth2) {
+    if (!c || !x || !y || !y2 || n < 2) return fail(ZPLT_EINVAL, "bad spline arguments");
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->spx), cudaFree(c->spy), cudaFree(c->spy2);
+    c->spx = c->spy = c->spy2 = nullptr;
+    int rc;
+    if ((rc = upload((void **) &c->spx, x, n * sizeof(double), c->stream))) return rc;
+    if ((rc = upload((void **) &c->spy, y, n * sizeof(double), c->stream))) return rc;
+    if ((rc = upload((void **) &c->spy2, y2, n * sizeof(double), c->stream))) return rc;
+    return build_power_table(c, 0, 0.0, n, normalization, Pk_smooth2);
+}
+
+extern "C" int zplt_set_power_law(zplt_ctx *c, double index, double normalization, double Pk_smooth2) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    return build_power_table(c, 1, index, 0, normalization, Pk_smooth2);
+}
+
+extern "C" int zplt_set_eigenmodes(zplt_ctx *c, int32_t ppd_e, const double *table) {
+    if (!c || !table || ppd_e < 2 || (ppd_e & 1)) return fail(ZPLT_EINVAL, "bad eigenmode table");
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->eig);
+    c->eig       = nullptr;
+    size_t bytes = (size_t) ppd_e * ppd_e * (ppd_e / 2 + 1) * 4 * sizeof(double);
+    int rc;
+    if ((rc = upload((void **) &c->eig, table, bytes, c->stream))) return rc;
+    c->gp.eig        = c->eig;
+    c->gp.pe         = ppd_e;
+    c->gp.eig_direct = (ppd_e % c->N == 0);
+    c->gp.eig_scale  = ((double) ppd_e) / c->N;
+    c->have_eig      = true;
+    return ZPLT_OK;
+}
+
+// ---------------------------------------------------------------- resources -------
+extern "C" size_t zplt_workspace_bytes(const zplt_ctx *c) { return c ? c->cube_bytes : 0; }
+
+extern "C" int zplt_set_workspace(zplt_ctx *c, void *p, size_t bytes) {
+    if (!c || !p) return fail(ZPLT_EINVAL, "null argument");
+    if (bytes < c->cube_bytes) return fail(ZPLT_EINVAL, "workspace too small: %zu < %zu", bytes, c->cube_bytes);
+    if (((uintptr_t) p) & 255) return fail(ZPLT_EINVAL, "workspace must be 256-byte aligned");
+    if (c->own_cube && c->cube) cudaFree(c->cube);
+    c->cube     = (cplx *) p;
+    c->own_cube = false;
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_set_stream(zplt_ctx *c, void *s) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream     = (cudaStream_t) s;
+    c->own_stream = false;
+    return ZPLT_OK;
+}
+
+static int ensure_cube(zplt_ctx *c) {
+    if (c->cube) return ZPLT_OK;
+    cudaError_t e = cudaMalloc((void **) &c->cube, c->cube_bytes);
+    if (e != cudaSuccess) {
+        c->cube = nullptr;
+        return fail(ZPLT_ENOMEM, "cudaMalloc of %zu workspace bytes failed: %s", c->cube_bytes, cudaGetErrorString(e));
+    }
+    c->own_cube = true;
+    return ZPLT_OK;
+}
+
+static int ready(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (!c->have_power) return fail(ZPLT_ESTATE, "power spectrum not set");
+    if (c->cfg.qPLT && !c->have_eig) return fail(ZPLT_ESTATE, "qPLT set but no eigenmode table given");
+    CK(cudaSetDevice(c->device));
+    return ensure_cube(c);
+}
+
+// ---------------------------------------------------------------- hot path --------
+static TileGeom geom_axis(int N, int na, int axis) {
+    // cube layout [a][z][y][x]; axis 2 = z (stride N^2), 1 = y (stride N), 0 = x rows
+    TileGeom g;
+    const int T = fft_tile_T(N);
+    g.astride   = (long long) N * N * N;
+    g.grid_z    = na;
+    g.pa        = T;
+    g.phi_stride = 0;
+    if (axis == 2) {
+        g.nstride = (long long) N * N, g.ostride = N, g.tstride = T, g.plo_stride = 1;
+        g.grid_x = N / T, g.grid_y = N;
+    } else if (axis == 1) {
+        g.nstride = N, g.ostride = (long long) N * N, g.tstride = T, g.plo_stride = 1;
+        g.grid_x = N / T, g.grid_y = N;
+    } else {
+        g.nstride = 1, g.ostride = (long long) N * N, g.tstride = (long long) T * N, g.plo_stride = N;
+        g.grid_x = N / T, g.grid_y = N;
+    }
+    return g;
+}
+
+static int run_generate(zplt_ctx *c, bool with_fft) {
+    int rc = ready(c);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev_gen[0], c->stream));
+    CK(launch_generate(c->gp, c->cube, c->stream));
+    CK(cudaEventRecord(c->ev_gen[1], c->stream));
+    c->launches[0] = 1;
+    c->launches[1] = c->launches[2] = c->launches[3] = 0;
+    if (with_fft) {
+        CK(launch_fft_tiles(c->N, c->cube, geom_axis(c->N, c->na, 2), c->tw, c->stream));
+        c->launches[1] = 1;
+    }
+    CK(cudaEventRecord(c->ev_gen[2], c->stream));
+    if (with_fft) {
+        CK(launch_fft_tiles(c->N, c->cube, geom_axis(c->N, c->na, 1), c->tw, c->stream));
+        c->launches[2] = 1;
+    }
+    CK(cudaEventRecord(c->ev_gen[3], c->stream));
+    c->n_emit_ev = 0;
+    c->generated = with_fft;
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_generate(zplt_ctx *c) { return run_generate(c, true); }
+
+extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *device_out) {
+    if (!c || !device_out) return fail(ZPLT_EINVAL, "null argument");
+    if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
+    if (z0 < 0 || nz <= 0 || z0 + nz > c->N) return fail(ZPLT_EINVAL, "plane range [%lld,%lld) outside [0,%d)", (long long) z0, (long long) (z0 + nz), c->N);
+    CK(cudaSetDevice(c->device));
+    EmitParams ep;
+    ep.icformat     = c->cfg.icformat;
+    ep.record_bytes = (int) zplt_record_bytes(c->cfg.icformat);
+    ep.na           = c->na;
+    ep.qPLT         = c->cfg.qPLT;
+    ep.vnorm        = c->vnorm;
+    ep.z0           = z0;
+    ep.out          = (unsigned char *) device_out;
+    ep.stats        = c->stats;
+    bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
+    if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
+    CK(launch_fft_emit(c->N, c->cube, z0, nz, ep, c->tw, c->stream, &c->launches[3]));
+    if (timed) {
+        CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev + 1], c->stream));
+        c->n_emit_ev++;
+    }
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_fetch_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *host_out) {
+    if (!c || !host_out) return fail(ZPLT_EINVAL, "null argument");
+    if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
+    if (z0 < 0 || nz <= 0 || z0 + nz > c->N) return fail(ZPLT_EINVAL, "plane range outside the lattice");
+    CK(cudaSetDevice(c->device));
+    const size_t plane = (size_t) c->N * c->N * zplt_record_bytes(c->cfg.icformat);
+    long long chunk    = (long long) ((256ull << 20) / plane);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nz) chunk = nz;
+    if (c->stage_bytes < (size_t) chunk * plane) {
+        for (int i = 0; i < 2; i++) {
+            if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
+            c->stage_dev[i] = nullptr;
+            CK(cudaMalloc((void **) &c->stage_dev[i], (size_t) chunk * plane));
+        }
+        c->stage_bytes = (size_t) chunk * plane;
+    }
+    int i = 0;
+    bool used[2] = {false, false};
+    for (long long z = z0; z < z0 + nz; z += chunk, i ^= 1) {
+        long long n = (z + chunk <= z0 + nz) ? chunk : (z0 + nz - z);
+        if (used[i]) CK(cudaStreamWaitEvent(c->stream, c->stage_free[i], 0));
+        int rc = zplt_emit_planes(c, z, n, c->stage_dev[i]);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->stage_full[i], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->stage_full[i], 0));
+        CK(cudaMemcpyAsync((unsigned char *) host_out + (size_t) (z - z0) * plane, c->stage_dev[i], (size_t) n * plane,
+                           cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(c->stage_free[i], c->copy_stream));
+        used[i] = true;
+    }
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_reset_stats(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->stats, 0, ZPLT_STAT_SLOTS * 8 * sizeof(double), c->stream));
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_get_stats(zplt_ctx *c, double *var, double md[3]) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    double h[ZPLT_STAT_SLOTS * 8];
+    CK(cudaMemcpyAsync(h, c->stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double v = 0, mp[3] = {0, 0, 0}, mn[3] = {0, 0, 0};
+    for (int s = 0; s < ZPLT_STAT_SLOTS; s++) {
+        v += h[8 * s];
+        for (int j = 0; j < 3; j++) {
+            if (h[8 * s + 1 + j] > mp[j]) mp[j] = h[8 * s + 1 + j];
+            if (h[8 * s + 4 + j] > mn[j]) mn[j] = h[8 * s + 4 + j];
+        }
+    }
+    if (var) *var = v;
+    // signed value of the largest |pos[j]| (reference src/output.cpp:190-193)
+    if (md)
+        for (int j = 0; j < 3; j++) md[j] = (mp[j] >= mn[j]) ? mp[j] : -mn[j];
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_synchronize(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_get_timings(zplt_ctx *c, double out[8]) {
+    if (!c || !out) return fail(ZPLT_EINVAL, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    for (int i = 0; i < 3; i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev_gen[i], c->ev_gen[i + 1]));
+        out[i] = ms;
+    }
+    for (int i = 0; i < c->n_emit_ev; i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev_emit[2 * i], c->ev_emit[2 * i + 1]));
+        out[3] += ms;
+    }
+    for (int i = 0; i < 4; i++) out[4 + i] = c->launches[i];
+    return ZPLT_OK;
+}
+
+// ---------------------------------------------------------------- introspection ---
+extern "C" int zplt_dbg_pcg_draws(uint64_t seed, uint64_t off_hi, uint64_t off_lo, int64_t n, uint64_t *host_out) {
+    if (!host_out || n <= 0) return fail(ZPLT_EINVAL, "bad arguments");
+    u128 s0  = pcg_seed_state(seed);
+    Affine j = pcg_jump(((unsigned __int128) off_hi << 64) | off_lo);
+    u128 *ds;
+    Affine *dj;
+    uint64_t *dout;
+    CK(cudaMalloc((void **) &ds, sizeof(u128)));
+    CK(cudaMalloc((void **) &dj, sizeof(Affine)));
+    CK(cudaMalloc((void **) &dout, n * sizeof(uint64_t)));
+    CK(cudaMemcpy(ds, &s0, sizeof(u128), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dj, &j, sizeof(Affine), cudaMemcpyHostToDevice));
+    CK(launch_pcg_draws(ds, dj, n, dout, 0));
+    CK(cudaMemcpy(host_out, dout, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    cudaFree(ds), cudaFree(dj), cudaFree(dout);
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_dbg_mode_draws(zplt_ctx *c, int64_t n, const int32_t *k, uint64_t *host_raw, double *host_u) {
+    if (!c || !k || !host_raw || !host_u || n <= 0) return fail(ZPLT_EINVAL, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    for (int64_t i = 0; i < n; i++) {
+        int kx = k[3 * i], ky = k[3 * i + 1], kz = k[3 * i + 2];
+        if (ky < 0 || ky >= c->N / 2 || kx < -c->N / 2 || kx > c->N / 2 || kz < -c->N / 2 || kz > c->N / 2)
+            return fail(ZPLT_EINVAL, "mode %lld outside the primary half-lattice", (long long) i);
+    }
+    int *dk;
+    uint64_t *dr;
+    double *du;
+    CK(cudaMalloc((void **) &dk, 3 * n * sizeof(int)));
+    CK(cudaMalloc((void **) &dr, 2 * n * sizeof(uint64_t)));
+    CK(cudaMalloc((void **) &du, 2 * n * sizeof(double)));
+    CK(cudaMemcpy(dk, k, 3 * n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(launch_mode_draws(c->gp, n, dk, dr, du, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(host_raw, dr, 2 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(host_u, du, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dk), cudaFree(dr), cudaFree(du);
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_dbg_power_table(zplt_ctx *c, int64_t count, double *host_out) {
+    if (!c || !host_out || count <= 0 || count > c->ptab_count) return fail(ZPLT_EINVAL, "bad arguments");
+    if (!c->have_power) return fail(ZPLT_ESTATE, "power spectrum not set");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(host_out, c->ptab, count * sizeof(double), cudaMemcpyDeviceToHost));
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_dbg_spectral(zplt_ctx *c, double *host_out) {
+    if (!host_out) return fail(ZPLT_EINVAL, "null argument");
+    int rc = run_generate(c, false);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(host_out, c->cube, c->cube_bytes, cudaMemcpyDeviceToHost));
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_dbg_after_generate(zplt_ctx *c, double *host_out) {
+    if (!c || !host_out) return fail(ZPLT_EINVAL, "null argument");
+    if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(host_out, c->cube, c->cube_bytes, cudaMemcpyDeviceToHost));
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *host_data) {
+    if (!host_data) return fail(ZPLT_EINVAL, "null argument");
+    const int T = fft_tile_T(n);
+    if (T == 0) return fail(ZPLT_EINVAL, "unsupported FFT length %d", n);
+    if (batch <= 0 || batch % T) return fail(ZPLT_EINVAL, "batch must be a positive multiple of %d for n=%d", T, n);
+    std::vector<cplx> tw(n);
+    for (int j = 0; j < n; j++) {
+        long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double) j / (long double) n;
+        tw[j]           = make_double2((double) cosl(ang), (double) sinl(ang));
+    }
+    cplx *dtw, *d;
+    size_t bytes = (size_t) n * batch * sizeof(cplx);
+    CK(cudaMalloc((void **) &dtw, n * sizeof(cplx)));
+    CK(cudaMalloc((void **) &d, bytes));
+    CK(cudaMemcpy(dtw, tw.data(), n * sizeof(cplx), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d, host_data, bytes, cudaMemcpyHostToDevice));
+    TileGeom g;
+    g.astride = 0, g.ostride = 0, g.grid_y = 1, g.grid_z = 1, g.pa = T, g.phi_stride = 0;
+    g.grid_x = (int) (batch / T);
+    if (row_mode) {
+        g.nstride = 1, g.plo_stride = n, g.tstride = (long long) T * n;
+    } else {
+        g.nstride = batch, g.plo_stride = 1, g.tstride = T;
+    }
+    CK(launch_fft_tiles(n, d, g, dtw, 0));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_data, d, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(d), cudaFree(dtw);
+    return ZPLT_OK;
+}
+
+// ---------------------------------------------------------------- internal hooks --
+// used by host/host_api.cpp (same shared object); not part of the public header
+extern "C" void zplt_set_error_(const char *msg) { g_err = msg ? msg : ""; }
+extern "C" int zplt_ctx_ppd_(const zplt_ctx *c) { return c ? c->N : 0; }
+extern "C" int zplt_ctx_icformat_(const zplt_ctx *c) { return c ? c->cfg.icformat : -1; }

@@ -1,0 +1,257 @@
+// Device-side building blocks of the mode generator: 128-bit PCG64 arithmetic, the
+// (0,1] mapping, Box-Muller, PLT eigenmode interpolation and the per-mode field
+// amplitudes.  sm_100a only.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zplt {
+
+typedef double2 cplx;  // .x = re, .y = im
+
+// ------------------------------------------------------------------ 128-bit LCG ----
+struct u128 {
+    uint64_t lo, hi;
+};
+// affine map s -> mult*s + plus (mod 2^128): a jump of the LCG by some number of draws
+struct Affine {
+    u128 mult, plus;
+};
+
+__host__ __device__ __forceinline__ u128 mul128(u128 a, u128 b) {
+    u128 r;
+    r.lo = a.lo * b.lo;
+#ifdef __CUDA_ARCH__
+    r.hi = __umul64hi(a.lo, b.lo) + a.hi * b.lo + a.lo * b.hi;
+#else
+    unsigned __int128 t = (unsigned __int128) a.lo * b.lo;
+    r.hi                = (uint64_t) (t >> 64) + a.hi * b.lo + a.lo * b.hi;
+#endif
+    return r;
+}
+__host__ __device__ __forceinline__ u128 add128(u128 a, u128 b) {
+    u128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+__host__ __device__ __forceinline__ u128 apply(const Affine &j, u128 s) { return add128(mul128(j.mult, s), j.plus); }
+
+// pcg64 = setseq_xsl_rr_128_64 with the default stream
+// (reference include/pcg-rng/pcg_random.hpp:159-170 constants, :370 bump, :381-386
+// operator() with output_previous=false, :1144-1170 xsl_rr output).
+#define ZPLT_PCG_MULT_HI 2549297995355413924ull
+#define ZPLT_PCG_MULT_LO 4865540595714422341ull
+#define ZPLT_PCG_INC_HI 6364136223846793005ull
+#define ZPLT_PCG_INC_LO 1442695040888963407ull
+
+__host__ __device__ __forceinline__ uint64_t pcg_next(u128 &s) {
+    const u128 M = {ZPLT_PCG_MULT_LO, ZPLT_PCG_MULT_HI};
+    const u128 C = {ZPLT_PCG_INC_LO, ZPLT_PCG_INC_HI};
+    s            = add128(mul128(s, M), C);
+    uint64_t x   = s.hi ^ s.lo;
+    unsigned rot = (unsigned) (s.hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+
+// one_rand<2> (reference src/power_spectrum.cpp:284-308): uint64 -> (0,1];
+// (double)(r+1) rounds to nearest even exactly as the host conversion does, and the
+// scale by 2^-64 is exact.
+__device__ __forceinline__ double u64_to_unit(uint64_t r) {
+    if (r == 0xffffffffffffffffull) return 1.0;
+    return __ull2double_rn(r + 1ull) * 0x1.0p-64;
+}
+
+// ------------------------------------------------------------------ parameters -----
+struct GenParams {
+    int N;        // ppd
+    int half;     // ppd/2
+    int kmax;     // (int)(half/k_cutoff + .5)       reference src/zeldovich.cpp:350
+    int na;       // packed arrays: 2 (ZA) or 4 (qPLT)
+    int corner_modes, qonemode, one_mode[3];
+    int qPLT, qPLTrescale, fixed_power;
+    double fundamental, fundamental2;  // 2*pi/L and its square (reference src/parameters.cpp:176, src/zeldovich.cpp:301)
+    double k2_cutoff;                  // nyquist^2/k_cutoff^2   (reference src/zeldovich.cpp:318-319)
+    double f_cluster, target_f, growth_ratio;  // target_f :305 ; growth_ratio = a_NL/a0 :307-312,428
+    // tables
+    const double *ptab;    // P at k = sqrt(m)*fundamental, m = kx^2+ky^2+kz^2
+    const u128 *ystate;    // [N/2] generator state at the start of plane ky (2*ky*65536^2 draws after seeding)
+    const Affine *zjump;   // [N]   jump by 2*65536*(kz mod 65536) draws, indexed by lattice z
+    const Affine *xjump;   // [N]   jump by 2*(kx mod 65536) draws, indexed by lattice x
+    const double *eig;     // [pe][pe][pe/2+1][4]
+    int pe;                // eigenmode table ppd
+    int eig_direct;        // pe % N == 0 -> direct lookup (reference src/zeldovich.cpp:161-170)
+    double eig_scale;      // (double)pe / N
+};
+
+struct Mode {
+    double Dr, Di;  // density mode D
+    double s0, s1, s2;  // F,G,H = i * s_c * D          (reference src/zeldovich.cpp:432-434)
+    double f;       // velocity factor                  (reference src/zeldovich.cpp:415)
+};
+
+__device__ __forceinline__ int wrap_k(int i, int N, int half) { return i > half ? i - N : i; }
+
+// interp_eigmode (reference src/zeldovich.cpp:154-227); ik* are table-convention indices in [0,N)
+__device__ __forceinline__ void interp_eig(const GenParams &g, int ikx, int iky, int ikz, double e[4]) {
+    const int pe   = g.pe;
+    const int hp1  = pe / 2 + 1;
+    const int half = pe / 2;
+    const double2 *tab2 = reinterpret_cast<const double2 *>(g.eig);
+    auto ld4 = [tab2](size_t i) {
+        double2 lo = __ldg(&tab2[2 * i]), hi = __ldg(&tab2[2 * i + 1]);
+        return make_double4(lo.x, lo.y, hi.x, hi.y);
+    };
+    if (g.eig_direct) {
+        const int q = pe / g.N;
+        double4 v   = ld4(((size_t) (ikx * q) * pe + (size_t) (iky * q)) * hp1 + (size_t) (ikz * q));
+        e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+        return;
+    }
+    int lo[3], hi[3];
+    double fr[3];
+    const int ik[3] = {ikx, iky, ikz};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double f = g.eig_scale * ik[d];
+        if (f > half && f < hp1) f = floor(f + 1);  // never interpolate across the Nyquist gap
+        lo[d] = (int) f;
+        hi[d] = lo[d] + 1;
+        if (hi[d] == pe) hi[d] = 0;
+        fr[d] = f - lo[d];
+    }
+    // the z corner one past the stored half axis is only reached with weight exactly 0
+    // (reference src/zeldovich.cpp:187-198); clamp so that no out-of-range load is issued
+    if (hi[2] > half) hi[2] = half;
+    double w[8];
+    w[0] = (1 - fr[0]) * (1 - fr[1]) * (1 - fr[2]);
+    w[1] = (1 - fr[0]) * (1 - fr[1]) * (fr[2]);
+    w[2] = (1 - fr[0]) * (fr[1]) * (1 - fr[2]);
+    w[3] = (1 - fr[0]) * (fr[1]) * (fr[2]);
+    w[4] = (fr[0]) * (1 - fr[1]) * (1 - fr[2]);
+    w[5] = (fr[0]) * (1 - fr[1]) * (fr[2]);
+    w[6] = (fr[0]) * (fr[1]) * (1 - fr[2]);
+    w[7] = (fr[0]) * (fr[1]) * (fr[2]);
+    double4 acc = make_double4(0, 0, 0, 0);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int cx    = (c & 4) ? hi[0] : lo[0];
+        int cy    = (c & 2) ? hi[1] : lo[1];
+        int cz    = (c & 1) ? hi[2] : lo[2];
+        double4 v = ld4(((size_t) cx * pe + (size_t) cy) * hp1 + (size_t) cz);
+        // plain multiply-then-add in corner order, as the reference's left-to-right sum
+        acc.x = (c == 0) ? __dmul_rn(w[c], v.x) : __dadd_rn(acc.x, __dmul_rn(w[c], v.x));
+        acc.y = (c == 0) ? __dmul_rn(w[c], v.y) : __dadd_rn(acc.y, __dmul_rn(w[c], v.y));
+        acc.z = (c == 0) ? __dmul_rn(w[c], v.z) : __dadd_rn(acc.z, __dmul_rn(w[c], v.z));
+        acc.w = (c == 0) ? __dmul_rn(w[c], v.w) : __dadd_rn(acc.w, __dmul_rn(w[c], v.w));
+    }
+    e[0] = acc.x, e[1] = acc.y, e[2] = acc.z, e[3] = acc.w;
+}
+
+// get_eigenmode (reference src/zeldovich.cpp:229-276): e = {vec0, vec1, vec2, val}
+__device__ __forceinline__ void get_eig(const GenParams &g, int kx, int ky, int kz, double e[4]) {
+    if (!g.qPLT) {
+        e[0] = kx, e[1] = ky, e[2] = kz, e[3] = 1.0;
+        return;
+    }
+    int ikx = kx < 0 ? g.N + kx : kx;
+    int iky = ky < 0 ? g.N + ky : ky;
+    int ikz = kz < 0 ? g.N + kz : kz;
+    ikz     = ikz > g.half ? g.N - ikz : ikz;  // stored half-space is +kz
+    double k2 = (double) (kx * kx + ky * ky + kz * kz);
+    double eh[4];
+    interp_eig(g, ikx, iky, ikz, eh);
+    if (kz < 0) eh[2] = -eh[2];
+    double mag = sqrt(eh[0] * eh[0] + eh[1] * eh[1] + eh[2] * eh[2]);
+    eh[0] /= mag;
+    eh[1] /= mag;
+    eh[2] /= mag;
+    double norm = k2 / (kx * eh[0] + ky * eh[1] + kz * eh[2]);
+    if (k2 == 0.0 || !isfinite(norm)) norm = 0.0;
+    e[0] = norm * eh[0];
+    e[1] = norm * eh[1];
+    e[2] = norm * eh[2];
+    e[3] = eh[3];
+}
+
+// Mask of reference src/zeldovich.cpp:350-358.  n2 = kx^2+ky^2+kz^2.
+__device__ __forceinline__ bool mode_masked(const GenParams &g, int kx, int ky, int kz, int n2) {
+    if (abs(kx) == g.kmax || abs(kz) == g.kmax || abs(ky) == g.kmax) return true;
+    if (!g.corner_modes && (double) n2 * g.fundamental2 >= g.k2_cutoff) return true;
+    if (g.qonemode && !(kx == g.one_mode[0] && ky == g.one_mode[1] && kz == g.one_mode[2])) return true;
+    return false;
+}
+
+// Generator state positioned at the first of the two draws of the primary mode whose
+// lattice indices are (x, y, z), 0 <= y < N/2 (reference nskip
+// bookkeeping src/zeldovich.cpp:335,341,358-363): 2*(ky*M^2 + (kz mod M)*M + (kx mod M)).
+__device__ __forceinline__ u128 mode_rng_state(const GenParams &g, int x, int y, int z) {
+    u128 s = g.ystate[y];
+    s      = apply(g.zjump[z], s);
+    s      = apply(g.xjump[x], s);
+    return s;
+}
+
+// cgauss<2> (reference src/power_spectrum.cpp:338-359) given the two uniform deviates
+__device__ __forceinline__ void box_muller(const GenParams &g, double P, double u1, double u2, double &Dr, double &Di) {
+    double R     = g.fixed_power ? sqrt(P) : sqrt(-P * log(u1));
+    double theta = 2 * 3.14159265358979323846 * u2;
+    double sn, cs;
+    sincos(theta, &sn, &cs);
+    Dr = R * cs;
+    Di = R * sn;
+}
+
+// The primary mode at lattice indices (x,y,z), 0 <= y < N/2
+// (reference LoadPlane body, src/zeldovich.cpp:331-438).
+__device__ __forceinline__ void primary_mode(const GenParams &g, int x, int y, int z, Mode &m) {
+    const int kx = wrap_k(x, g.N, g.half), ky = y, kz = wrap_k(z, g.N, g.half);
+    const int n2 = kx * kx + ky * ky + kz * kz;
+    m.Dr = m.Di = m.s0 = m.s1 = m.s2 = m.f = 0.0;
+    if (mode_masked(g, kx, ky, kz, n2)) return;
+    u128 s    = mode_rng_state(g, x, y, z);
+    double u1 = u64_to_unit(pcg_next(s));
+    double u2 = u64_to_unit(pcg_next(s));
+    double P  = __ldg(&g.ptab[n2]);
+    box_muller(g, P, u1, u2, m.Dr, m.Di);
+    if (m.Dr == 0.0 && m.Di == 0.0) return;  // "D != 0." guard (reference src/zeldovich.cpp:403)
+    double k2 = (double) n2 * g.fundamental2;
+    if (k2 == 0.0) k2 = 1.0;
+    double ik2 = 1. / k2;
+    double e[4];
+    get_eig(g, kx, ky, kz, e);
+    double rescale = 1., f = 1.0;
+    if (g.qPLT) {
+        f = (sqrt(1. + 24 * e[3] * g.f_cluster) - 1) * .25;
+        if (g.qPLTrescale) rescale = pow(g.growth_ratio, g.target_f - f);
+    }
+    m.s0 = rescale * e[0] * g.fundamental * ik2;
+    m.s1 = rescale * e[1] * g.fundamental * ik2;
+    m.s2 = rescale * e[2] * g.fundamental * ik2;
+    m.f  = f;
+}
+
+// Packed entries A0..A3 for the primary site and for its conjugate-structured twin
+// (reference src/zeldovich.cpp:447-466).
+__device__ __forceinline__ void pack_primary(const Mode &m, cplx a[4]) {
+    const double Fr = -m.s0 * m.Di, Fi = m.s0 * m.Dr;
+    const double Gr = -m.s1 * m.Di, Gi = m.s1 * m.Dr;
+    const double Hr = -m.s2 * m.Di, Hi = m.s2 * m.Dr;
+    const double f = m.f;
+    a[0] = make_double2(m.Dr - Fi, m.Di + Fr);
+    a[1] = make_double2(Gr - Hi, Gi + Hr);
+    a[2] = make_double2(0. - Fi * f, 0. + Fr * f);
+    a[3] = make_double2(Gr * f - Hi * f, Gi * f + Hr * f);
+}
+__device__ __forceinline__ void pack_twin(const Mode &m, cplx a[4]) {
+    const double Fr = -m.s0 * m.Di, Fi = m.s0 * m.Dr;
+    const double Gr = -m.s1 * m.Di, Gi = m.s1 * m.Dr;
+    const double Hr = -m.s2 * m.Di, Hi = m.s2 * m.Dr;
+    const double f = m.f;
+    a[0] = make_double2(m.Dr + Fi, -m.Di + Fr);
+    a[1] = make_double2(Gr + Hi, -Gi + Hr);
+    a[2] = make_double2(0. + Fi * f, 0. + Fr * f);
+    a[3] = make_double2(Gr * f + Hi * f, -(Gi * f) + Hr * f);
+}
+
+}  // namespace zplt

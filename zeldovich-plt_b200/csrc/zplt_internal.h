@@ -1,0 +1,53 @@
+// Internal launcher prototypes shared by the translation units of libzeldovich_b200.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "zplt_device.cuh"
+
+namespace zplt {
+
+// Where a tile of pencils lives in memory, all in units of complex elements.
+// Pencil p of the tile starts at  base + (p % pa)*plo_stride + (p / pa)*phi_stride,
+// its n-th point is nstride further.  base = blockIdx.z*astride + blockIdx.y*ostride
+// + blockIdx.x*tstride.
+struct TileGeom {
+    long long astride, ostride, tstride;
+    long long plo_stride, phi_stride, nstride;
+    int pa;
+    int grid_x, grid_y, grid_z;
+};
+
+struct EmitParams {
+    int icformat;
+    int record_bytes;
+    int na;             // arrays (2 or 4)
+    int qPLT;
+    double vnorm;       // velocity factor when !qPLT (reference src/output.cpp:78-82)
+    long long z0;       // first plane of this launch (records are written relative to it)
+    unsigned char *out; // records, (z - z0, y, x) order
+    double *stats;      // [ZPLT_STAT_SLOTS][8]: sum dens^2, +max[3], -max[3], pad
+};
+#define ZPLT_STAT_SLOTS 64
+
+int fft_tile_T(int N);            // pencils per CTA used for length N (strided / row kernels)
+size_t fft_tile_smem(int N, int T);
+// In-place backward FFT of every pencil described by geom.  Returns cudaError_t.
+int launch_fft_tiles(int N, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+// x-axis FFT of rows + record emission for planes [z0, z0+nz) of a [na][N][N][N] cube.
+int launch_fft_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
+                    cudaStream_t st, int *launches);
+
+int launch_power_table(double *ptab, long long count, double fundamental2, int is_powerlaw, double index, int n,
+                       const double *x, const double *y, const double *y2, double normalization, double smooth2,
+                       cudaStream_t st);
+int launch_generate(const GenParams &g, cplx *cube, cudaStream_t st);
+int launch_pcg_draws(const u128 *ystate0, const Affine *jump, long long n, uint64_t *out, cudaStream_t st);
+int launch_mode_draws(const GenParams &g, long long n, const int *k, uint64_t *raw, double *u, cudaStream_t st);
+
+// host helpers (zplt_tables.cpp part of api)
+u128 pcg_seed_state(uint64_t seed);
+Affine pcg_jump(unsigned __int128 delta);
+
+}  // namespace zplt

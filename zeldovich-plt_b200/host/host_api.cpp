@@ -1,0 +1,340 @@
+// Host half of the C ABI: parameter loading, power-spectrum set-up, eigenmode file
+// loading, ic_* file writing and the whole `zeldovich <param_file>` flow.  The device
+// half lives in csrc/zplt_api.cu; this file only talks to it through the C ABI.
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/zeldovich_b200.h"
+#include "host_parameters.h"
+#include "host_power.h"
+
+// error channel shared with the device half
+extern "C" void zplt_set_error_(const char *msg);
+
+static int hfail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    zplt_set_error_(buf);
+    return code;
+}
+
+static void put_str(char *dst, size_t cap, const std::string &s) {
+    snprintf(dst, cap, "%s", s.c_str());
+}
+
+static void to_pod(const Parameters &P, zplt_params *o) {
+    memset(o, 0, sizeof(*o));
+    o->boxsize = P.boxsize, o->Pk_scale = P.Pk_scale, o->separation = P.separation, o->fundamental = P.fundamental;
+    o->nyquist = P.nyquist, o->k_cutoff = P.k_cutoff, o->Pk_norm = P.Pk_norm, o->Pk_sigma = P.Pk_sigma;
+    o->Pk_sigma_ratio = P.Pk_sigma_ratio, o->f_cluster = P.f_cluster, o->Pk_smooth = P.Pk_smooth;
+    o->Pk_powerlaw_index = P.Pk_powerlaw_index, o->z_initial = P.z_initial, o->PLT_target_z = P.PLT_target_z;
+    o->f_NL = P.f_NL, o->n_s = P.n_s, o->Omega_M = P.Omega_M;
+    o->ppd = P.ppd, o->np = P.np, o->cpd = P.cpd, o->numblock = P.numblock, o->qdensity = P.qdensity, o->qascii = P.qascii;
+    o->qoneslab = P.qoneslab, o->seed = P.seed, o->qPk_fix_to_mean = P.qPk_fix_to_mean, o->qonemode = P.qonemode;
+    for (int i = 0; i < 3; i++) o->one_mode[i] = (size_t) i < P.one_mode.size() ? P.one_mode[i] : 0;
+    o->qPLT = P.qPLT, o->qPLTrescale = P.qPLTrescale, o->AllowDirectIO = P.AllowDirectIO, o->version = P.version;
+    o->CornerModes = P.CornerModes;
+    put_str(o->Pk_filename, sizeof(o->Pk_filename), P.Pk_filename.string());
+    put_str(o->output_dir, sizeof(o->output_dir), P.output_dir.string());
+    put_str(o->density_filename, sizeof(o->density_filename), P.density_filename.string());
+    put_str(o->PLT_filename, sizeof(o->PLT_filename), P.PLT_filename.string());
+    put_str(o->ICFormat, sizeof(o->ICFormat), P.ICFormat);
+}
+
+extern "C" int zplt_params_load(const char *param_file, zplt_params *out) {
+    if (!param_file || !out) return hfail(ZPLT_EINVAL, "null argument");
+    try {
+        Parameters P(param_file);
+        to_pod(P, out);
+    } catch (const std::exception &e) {
+        return hfail(ZPLT_EINVAL, "%s", e.what());
+    }
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_icformat_code(const char *f) {
+    if (!f) return -1;
+    if (!strcmp(f, "RVdoubleZel")) return ZPLT_FMT_RVDOUBLEZEL;
+    if (!strcmp(f, "RVZel")) return ZPLT_FMT_RVZEL;
+    if (!strcmp(f, "Zeldovich")) return ZPLT_FMT_ZELDOVICH;
+    if (!strcmp(f, "ZelSimple")) return ZPLT_FMT_ZELSIMPLE;
+    return -1;
+}
+
+extern "C" int zplt_config_from_params(const zplt_params *p, zplt_config *c) {
+    if (!p || !c) return hfail(ZPLT_EINVAL, "null argument");
+    memset(c, 0, sizeof(*c));
+    int fmt = zplt_icformat_code(p->ICFormat);
+    if (fmt < 0) return hfail(ZPLT_EINVAL, "Error: unknown ICFormat \"%s\". Aborting.", p->ICFormat);
+    if (p->f_NL != 0.) return hfail(ZPLT_EINVAL, "ZD_f_NL != 0 (primordial non-Gaussianity) is outside the B200 hot path");
+    if (p->qdensity != 0) return hfail(ZPLT_EINVAL, "ZD_qdensity output is not built yet");
+    c->ppd          = p->ppd;
+    c->boxsize      = p->boxsize;
+    c->seed         = (int64_t) p->seed;  // int -> unsigned long sign-extends (reference src/power_spectrum.cpp:14)
+    c->k_cutoff     = p->k_cutoff;
+    c->corner_modes = p->CornerModes;
+    c->qonemode     = p->qonemode;
+    for (int i = 0; i < 3; i++) c->one_mode[i] = p->one_mode[i];
+    c->qPLT         = p->qPLT;
+    c->qPLTrescale  = p->qPLTrescale;
+    c->fixed_power  = p->qPk_fix_to_mean;
+    c->PLT_target_z = p->PLT_target_z;
+    c->z_initial    = p->z_initial;
+    c->f_cluster    = p->f_cluster;
+    c->icformat     = fmt;
+    c->device       = -1;
+    c->rank         = 0;
+    c->nranks       = 1;
+    return ZPLT_OK;
+}
+
+// ---------------------------------------------------------------- power -----------
+struct zplt_power {
+    PowerSpectrum pk;
+};
+
+static PkParams pk_params(const zplt_params *p) {
+    PkParams q;
+    q.boxsize = p->boxsize, q.Pk_scale = p->Pk_scale, q.Pk_norm = p->Pk_norm, q.Pk_sigma = p->Pk_sigma;
+    q.Pk_sigma_ratio = p->Pk_sigma_ratio, q.Pk_smooth = p->Pk_smooth, q.qPk_fix_to_mean = p->qPk_fix_to_mean;
+    return q;
+}
+
+extern "C" int zplt_power_create(const zplt_params *p, zplt_power **out) {
+    if (!p || !out) return hfail(ZPLT_EINVAL, "null argument");
+    *out = nullptr;
+    zplt_power *h = new zplt_power();
+    try {
+        int rc;
+        if (p->Pk_filename[0])
+            rc = h->pk.InitFromFile(p->Pk_filename, pk_params(p));
+        else
+            rc = h->pk.InitFromPowerLaw(p->Pk_powerlaw_index, pk_params(p));
+        if (rc) {
+            delete h;
+            return hfail(ZPLT_EINVAL, "could not initialise the power spectrum from \"%s\"", p->Pk_filename);
+        }
+    } catch (const std::exception &e) {
+        delete h;
+        return hfail(ZPLT_EINVAL, "%s", e.what());
+    }
+    *out = h;
+    return ZPLT_OK;
+}
+extern "C" void zplt_power_destroy(zplt_power *h) { delete h; }
+extern "C" int zplt_power_info(const zplt_power *h, int32_t *n, double *norm, double *sm2) {
+    if (!h) return hfail(ZPLT_EINVAL, "null argument");
+    if (n) *n = h->pk.is_powerlaw ? 0 : h->pk.size();
+    if (norm) *norm = h->pk.normalization;
+    if (sm2) *sm2 = h->pk.Pk_smooth2;
+    return ZPLT_OK;
+}
+extern "C" int zplt_power_arrays(const zplt_power *h, double *x, double *y, double *y2) {
+    if (!h || !x || !y || !y2) return hfail(ZPLT_EINVAL, "null argument");
+    const int n = h->pk.size();
+    memcpy(x, h->pk.x.data(), n * sizeof(double));
+    memcpy(y, h->pk.y.data(), n * sizeof(double));
+    memcpy(y2, h->pk.y2.data(), n * sizeof(double));
+    return ZPLT_OK;
+}
+extern "C" double zplt_power_eval(zplt_power *h, double k) { return h ? h->pk.power(k) : 0.0; }
+extern "C" double zplt_power_sigmaR(zplt_power *h, double R) {
+    try {
+        return h ? h->pk.sigmaR(R) : 0.0;
+    } catch (const std::exception &e) {
+        hfail(ZPLT_EINVAL, "%s", e.what());
+        return -1.0;
+    }
+}
+extern "C" int zplt_power_apply(zplt_power *h, zplt_ctx *ctx) {
+    if (!h || !ctx) return hfail(ZPLT_EINVAL, "null argument");
+    if (h->pk.is_powerlaw) return zplt_set_power_law(ctx, h->pk.powerlaw_index, h->pk.normalization, h->pk.Pk_smooth2);
+    return zplt_set_power_spline(ctx, h->pk.size(), h->pk.x.data(), h->pk.y.data(), h->pk.y2.data(), h->pk.normalization,
+                                 h->pk.Pk_smooth2);
+}
+
+// ---------------------------------------------------------------- eigenmodes ------
+extern "C" int zplt_load_eigenmodes_file(zplt_ctx *ctx, const char *path) {
+    if (!ctx || !path) return hfail(ZPLT_EINVAL, "null argument");
+    fprintf(stderr, "Using PLT eigenmodes.\n");
+    std::ifstream f(path, std::ios::in | std::ios::binary | std::ios::ate);
+    if (!f) return hfail(ZPLT_EINVAL, "[Error] Could not open eigenmode file \"%s\".", path);
+    const std::streamoff size = f.tellg();
+    f.seekg(0, std::ios::beg);
+    int32_t ppd_e = 0;
+    f.read((char *) &ppd_e, sizeof(ppd_e));
+    if (!f || ppd_e <= 0 || ppd_e > 4096) return hfail(ZPLT_EINVAL, "[Error] Eigenmode file \"%s\" has a bad header.", path);
+    const size_t nelem  = (size_t) ppd_e * ppd_e * (ppd_e / 2 + 1) * 4;
+    const size_t nbytes = nelem * sizeof(double);
+    if ((size_t) size != nbytes + sizeof(ppd_e))
+        return hfail(ZPLT_EINVAL, "[Error] Eigenmode file \"%s\" of size %lld did not match expected size %zu from eig_vecs_ppd %d.", path,
+                     (long long) size, nbytes, ppd_e);
+    std::vector<double> tab(nelem);
+    f.read((char *) tab.data(), nbytes);
+    if (!f) return hfail(ZPLT_EINVAL, "[Error] short read on eigenmode file \"%s\".", path);
+    return zplt_set_eigenmodes(ctx, ppd_e, tab.data());
+}
+
+// ---------------------------------------------------------------- ic_* files ------
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct WriteStats {
+    int64_t files = 0, bytes = 0;
+    double seconds = 0;
+};
+
+static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, WriteStats *ws) {
+    fs::path dir(output_dir);
+    std::error_code ec;
+    if (fs::exists(dir, ec)) {
+        for (const auto &entry : fs::directory_iterator(dir, ec)) {
+            if (!entry.is_regular_file()) continue;
+            const std::string fn = entry.path().filename().string();
+            if (fn.compare(0, 3, "ic_") == 0 || fn.compare(0, 10, "zeldovich.") == 0) fs::remove(entry.path(), ec);
+        }
+    }
+    fs::create_directories(dir, ec);
+    if (ec) return hfail(ZPLT_EINVAL, "cannot create output directory \"%s\"", output_dir);
+
+    const size_t rb    = zplt_record_bytes(icformat);
+    const size_t plane = (size_t) ppd * ppd * rb;
+    int64_t chunk      = (int64_t) ((512ull << 20) / plane);
+    if (chunk < 1) chunk = 1;
+    if (chunk > ppd) chunk = ppd;
+    std::vector<unsigned char> buf((size_t) chunk * plane);
+    int64_t last_file = -1;
+    FILE *fp          = nullptr;
+    for (int64_t z0 = 0; z0 < ppd; z0 += chunk) {
+        const int64_t nz = (z0 + chunk <= ppd) ? chunk : ppd - z0;
+        int rc           = zplt_fetch_planes(ctx, z0, nz, buf.data());
+        if (rc) {
+            if (fp) fclose(fp);
+            return rc;
+        }
+        const double t0 = now_s();
+        for (int64_t z = z0; z < z0 + nz; z++) {
+            const int64_t fileno = z * cpd / ppd;  // integer division, reference src/output.cpp:208
+            if (fileno != last_file) {
+                if (fp) fclose(fp);
+                fs::path fn = dir / ("ic_" + std::to_string(fileno));
+                fp          = fopen(fn.c_str(), "ab");
+                if (!fp) return hfail(ZPLT_EINVAL, "cannot open \"%s\" for append", fn.c_str());
+                last_file = fileno;
+                if (ws) ws->files++;
+            }
+            if (fwrite(buf.data() + (size_t) (z - z0) * plane, 1, plane, fp) != plane) {
+                fclose(fp);
+                return hfail(ZPLT_EINVAL, "short write on ic file %lld", (long long) fileno);
+            }
+            if (ws) ws->bytes += (int64_t) plane;
+        }
+        if (ws) ws->seconds += now_s() - t0;
+    }
+    if (fp) fclose(fp);
+    return ZPLT_OK;
+}
+
+// The context does not expose its config through the ABI; keep what the writer needs here.
+extern "C" int zplt_ctx_ppd_(const zplt_ctx *ctx);
+extern "C" int zplt_ctx_icformat_(const zplt_ctx *ctx);
+
+extern "C" int zplt_write_ic_files(zplt_ctx *ctx, const char *output_dir, int32_t cpd) {
+    if (!ctx || !output_dir) return hfail(ZPLT_EINVAL, "null argument");
+    return write_ic_files(ctx, zplt_ctx_ppd_(ctx), zplt_ctx_icformat_(ctx), output_dir, cpd, nullptr);
+}
+
+// ---------------------------------------------------------------- whole run -------
+extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32_t write_files, zplt_run_report *rep) {
+    if (!param_file) return hfail(ZPLT_EINVAL, "null argument");
+    const double t_start = now_s();
+    zplt_run_report local;
+    if (!rep) rep = &local;
+    memset(rep, 0, sizeof(*rep));
+
+    zplt_params P;
+    int rc = zplt_params_load(param_file, &P);
+    if (rc) return rc;
+    zplt_power *pk = nullptr;
+    if ((rc = zplt_power_create(&P, &pk))) return rc;
+    zplt_config cfg;
+    if ((rc = zplt_config_from_params(&P, &cfg))) {
+        zplt_power_destroy(pk);
+        return rc;
+    }
+    cfg.device    = device;
+    zplt_ctx *ctx = nullptr;
+    if ((rc = zplt_create(&cfg, &ctx))) {
+        zplt_power_destroy(pk);
+        return rc;
+    }
+    auto bail = [&](int code) {
+        zplt_destroy(ctx);
+        zplt_power_destroy(pk);
+        return code;
+    };
+    if ((rc = zplt_power_apply(pk, ctx))) return bail(rc);
+    if (P.qPLT && (rc = zplt_load_eigenmodes_file(ctx, P.PLT_filename))) return bail(rc);
+    if (P.k_cutoff != 1)
+        fprintf(stderr, "Using k_cutoff = %f (effective ppd = %d)\n", P.k_cutoff, (int) (P.ppd / P.k_cutoff + .5));
+    rep->seconds_preamble = now_s() - t_start;
+    fprintf(stderr, "Preamble took %f seconds\n", rep->seconds_preamble);
+
+    const double t_dev = now_s();
+    if ((rc = zplt_generate(ctx))) return bail(rc);
+    WriteStats ws;
+    if (write_files) {
+        if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, &ws))) return bail(rc);
+    } else {
+        // still run the emission (statistics) without keeping the records
+        const size_t plane = (size_t) P.ppd * P.ppd * zplt_record_bytes(cfg.icformat);
+        int64_t chunk      = (int64_t) ((512ull << 20) / plane);
+        if (chunk < 1) chunk = 1;
+        if (chunk > P.ppd) chunk = P.ppd;
+        std::vector<unsigned char> buf((size_t) chunk * plane);
+        for (int64_t z0 = 0; z0 < P.ppd; z0 += chunk) {
+            int64_t nz = (z0 + chunk <= P.ppd) ? chunk : P.ppd - z0;
+            if ((rc = zplt_fetch_planes(ctx, z0, nz, buf.data()))) return bail(rc);
+        }
+    }
+    if ((rc = zplt_synchronize(ctx))) return bail(rc);
+    rep->seconds_device = now_s() - t_dev - ws.seconds;
+    rep->seconds_write  = ws.seconds;
+    double tm[8];
+    if ((rc = zplt_get_timings(ctx, tm))) return bail(rc);
+    for (int i = 0; i < 4; i++) rep->stage_ms[i] = tm[i];
+    if ((rc = zplt_get_stats(ctx, &rep->density_variance, rep->max_disp))) return bail(rc);
+    rep->ppd           = P.ppd;
+    rep->files_written = ws.files;
+    rep->bytes_written = ws.bytes;
+    rep->rms_density   = sqrt(rep->density_variance / ((double) P.ppd * P.ppd * P.ppd));
+    rep->input_sigma   = 0;
+    // the stderr summary of reference src/zeldovich.cpp:987-1011
+    fprintf(stderr, "The rms density variation of the pixels is %f\n", rep->rms_density);
+    rep->sigma_prediction = zplt_power_sigmaR(pk, P.separation / 4.0) * pow(P.boxsize, 1.5);
+    fprintf(stderr, "This could be compared to the P(k) prediction of %f\n", rep->sigma_prediction);
+    fprintf(stderr, "The maximum component-wise displacements are (%g, %g, %g), same units as BoxSize.\n", rep->max_disp[0],
+            rep->max_disp[1], rep->max_disp[2]);
+    fprintf(stderr,
+            "For Abacus' 2LPT implementation to work (assuming FINISH_WAIT_RADIUS = 1),\n\tthis implies a maximum CPD of %d\n",
+            (int) (P.boxsize / (2 * fabs(rep->max_disp[2]))));
+    fprintf(stderr, "Device stages: generate %.3f ms, z-FFT %.3f ms, y-FFT %.3f ms, x-FFT+emit %.3f ms\n", tm[0], tm[1], tm[2], tm[3]);
+    if (write_files)
+        fprintf(stderr, "Writing ic files took %.3g sec to write %.3g MB ==> %.3g MB/sec\n", ws.seconds, ws.bytes / 1e6,
+                ws.bytes / 1e6 / (ws.seconds > 0 ? ws.seconds : 1e-9));
+    rep->seconds_total = now_s() - t_start;
+    fprintf(stderr, "zeldovich took %.4g sec for ppd %lld ==> %.3g Mpart/sec\n", rep->seconds_total, (long long) P.ppd,
+            (double) P.np / 1e6 / rep->seconds_total);
+    bail(0);
+    return ZPLT_OK;
+}
