@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzeldovich_b200.so")
+LIB_PATH = os.environ.get("ZPLT_LIB") or os.path.join(HERE, "libzeldovich_b200.so")
 CLI_PATH = os.path.join(HERE, "bin", "zeldovich")
 
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, 1, 2, 3, 4

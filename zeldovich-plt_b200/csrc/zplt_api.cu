@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -144,6 +145,7 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     CK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return fail(ZPLT_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
 
+    if (const char *e = getenv("ZPLT_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) atoi(e));
     zplt_ctx *c = new zplt_ctx();
     memset(c, 0, sizeof(*c));
     c->cfg    = *cfg;
@@ -187,6 +189,7 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
         a0   = 1. / (1 + cfg->z_initial);
     }
     g.growth_ratio = a_NL / a0;
+    g.log_growth_ratio = log(g.growth_ratio);
     c->vnorm       = cfg->qPLT ? 1.0 : (sqrt(1. + 24 * cfg->f_cluster) - 1) * .25;  // src/output.cpp:78-82
 
     // RNG tables (reference src/power_spectrum.cpp:26-37 per-plane generators, and the
@@ -367,18 +370,29 @@ static TileGeom geom_axis(int N, int na, int axis) {
 static int run_generate(zplt_ctx *c, bool with_fft) {
     int rc = ready(c);
     if (rc) return rc;
+    c->launches[0] = c->launches[1] = c->launches[2] = c->launches[3] = 0;
     CK(cudaEventRecord(c->ev_gen[0], c->stream));
-    CK(launch_generate(c->gp, c->cube, c->stream));
+    const int gt = with_fft ? gen_xfft_T(c->N, c->na) : 0;
+    if (gt) {
+        // fused: draw the modes and transform the x axis in one kernel
+        CK(launch_gen_xfft(c->N, gt, c->gp, c->cube, c->tw, c->stream));
+        c->launches[0] = 1;
+    } else {
+        CK(launch_generate(c->gp, c->cube, c->stream));
+        c->launches[0] = 1;
+        if (with_fft) {
+            CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 0), c->tw, c->stream));
+            c->launches[0] = 2;
+        }
+    }
     CK(cudaEventRecord(c->ev_gen[1], c->stream));
-    c->launches[0] = 1;
-    c->launches[1] = c->launches[2] = c->launches[3] = 0;
     if (with_fft) {
-        CK(launch_fft_tiles(c->N, c->cube, geom_axis(c->N, c->na, 2), c->tw, c->stream));
+        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 2), c->tw, c->stream));
         c->launches[1] = 1;
     }
     CK(cudaEventRecord(c->ev_gen[2], c->stream));
     if (with_fft) {
-        CK(launch_fft_tiles(c->N, c->cube, geom_axis(c->N, c->na, 1), c->tw, c->stream));
+        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 1), c->tw, c->stream));
         c->launches[2] = 1;
     }
     CK(cudaEventRecord(c->ev_gen[3], c->stream));
@@ -405,7 +419,7 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
     ep.stats        = c->stats;
     bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
     if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
-    CK(launch_fft_emit(c->N, c->cube, z0, nz, ep, c->tw, c->stream, &c->launches[3]));
+    CK(launch_emit(c->N, c->cube, z0, nz, ep, c->stream, &c->launches[3]));
     if (timed) {
         CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev + 1], c->stream));
         c->n_emit_ev++;
@@ -596,7 +610,7 @@ extern "C" int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *
     } else {
         g.nstride = batch, g.plo_stride = 1, g.tstride = T;
     }
-    CK(launch_fft_tiles(n, d, g, dtw, 0));
+    CK(launch_fft_tiles(n, T, d, g, dtw, 0));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_data, d, bytes, cudaMemcpyDeviceToHost));
     cudaFree(d), cudaFree(dtw);

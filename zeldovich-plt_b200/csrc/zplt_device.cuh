@@ -73,6 +73,7 @@ struct GenParams {
     double fundamental, fundamental2;  // 2*pi/L and its square (reference src/parameters.cpp:176, src/zeldovich.cpp:301)
     double k2_cutoff;                  // nyquist^2/k_cutoff^2   (reference src/zeldovich.cpp:318-319)
     double f_cluster, target_f, growth_ratio;  // target_f :305 ; growth_ratio = a_NL/a0 :307-312,428
+    double log_growth_ratio;                   // log(a_NL/a0)
     // tables
     const double *ptab;    // P at k = sqrt(m)*fundamental, m = kx^2+ky^2+kz^2
     const u128 *ystate;    // [N/2] generator state at the start of plane ky (2*ky*65536^2 draws after seeding)
@@ -223,7 +224,9 @@ __device__ __forceinline__ void primary_mode(const GenParams &g, int x, int y, i
     double rescale = 1., f = 1.0;
     if (g.qPLT) {
         f = (sqrt(1. + 24 * e[3] * g.f_cluster) - 1) * .25;
-        if (g.qPLTrescale) rescale = pow(g.growth_ratio, g.target_f - f);
+        // pow(a_NL/a0, target_f - f) (reference src/zeldovich.cpp:428) as exp(log(ratio)*(target_f - f)):
+        // |exponent| <~ 0.1, so the two agree to a few 1e-16 relative
+        if (g.qPLTrescale) rescale = exp(g.log_growth_ratio * (g.target_f - f));
     }
     m.s0 = rescale * e[0] * g.fundamental * ik2;
     m.s1 = rescale * e[1] * g.fundamental * ik2;
@@ -254,4 +257,29 @@ __device__ __forceinline__ void pack_twin(const Mode &m, cplx a[4]) {
     a[3] = make_double2(Gr * f + Hi * f, -(Gi * f) + Hr * f);
 }
 
+}  // namespace zplt
+
+namespace zplt {
+// One packed array's entry (a = 0..3) from the stored mode state, primary or twin form
+// (same expressions as pack_primary / pack_twin, one component at a time).
+__device__ __forceinline__ cplx pack_one(double Dr, double Di, double s0, double s1, double s2, double f, int a, bool twin) {
+    const double Fr = -s0 * Di, Fi = s0 * Dr;
+    const double Gr = -s1 * Di, Gi = s1 * Dr;
+    const double Hr = -s2 * Di, Hi = s2 * Dr;
+    if (!twin) {
+        switch (a) {
+            case 0: return make_double2(Dr - Fi, Di + Fr);
+            case 1: return make_double2(Gr - Hi, Gi + Hr);
+            case 2: return make_double2(0. - Fi * f, 0. + Fr * f);
+            default: return make_double2(Gr * f - Hi * f, Gi * f + Hr * f);
+        }
+    } else {
+        switch (a) {
+            case 0: return make_double2(Dr + Fi, -Di + Fr);
+            case 1: return make_double2(Gr + Hi, -Gi + Hr);
+            case 2: return make_double2(0. + Fi * f, 0. + Fr * f);
+            default: return make_double2(Gr * f + Hi * f, -(Gi * f) + Hr * f);
+        }
+    }
+}
 }  // namespace zplt

@@ -7,13 +7,44 @@
 //                    (reference src/output.cpp:41-234): unpack Re/Im of the packed arrays
 //                    into displacement/velocity, cast to the ICFormat record, accumulate
 //                    density_variance and max_disp.
+#include <cstdlib>
+
+#ifndef ZPLT_LDHINT
+#define ZPLT_LDHINT 1
+#endif
+#ifndef ZPLT_STHINT
+#define ZPLT_STHINT 1
+#endif
 #include "zplt_fft.cuh"
 #include "zplt_internal.h"
 
 namespace zplt {
 
+// streaming (read-once / write-once) global accesses: do not keep the lines in L1
+__device__ __forceinline__ cplx ld_stream(const cplx *p) {
+    cplx r;
+#if ZPLT_LDHINT == 1
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#elif ZPLT_LDHINT == 2
+    r = __ldcs(p);
+#else
+    r = *p;
+#endif
+    return r;
+}
+__device__ __forceinline__ void st_stream(cplx *p, cplx v) {
+#if ZPLT_STHINT == 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
+// resident CTAs per SM the register budget is tuned for: 512 threads of 128 registers fill an SM
+constexpr int min_ctas(int threads) { return threads >= 512 ? 1 : (512 / threads > 8 ? 8 : 512 / threads); }
+
 template <int N, int T>
-__global__ void __launch_bounds__(T *(N / 16)) fft_tile_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw) {
+__global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *S         = reinterpret_cast<cplx *>(smem_raw);
     constexpr int M = N / 16;
@@ -23,10 +54,107 @@ __global__ void __launch_bounds__(T *(N / 16)) fft_tile_kernel(cplx *__restrict_
                            (long long) (p / g.pa) * g.phi_stride;
     cplx v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = data[base + (long long) (b + M * e) * g.nstride];
+    for (int e = 0; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
     fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
 #pragma unroll
-    for (int e = 0; e < 16; e++) data[base + (long long) (b + M * e) * g.nstride] = v[e];
+    for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (b + M * e) * g.nstride], v[e]);
+}
+
+// ------------------------------------------------------------------ generation + x FFT
+// Fused mode generation and x-axis FFT (the first of the three axes; the transform is
+// separable so the axis order is free).  One CTA owns R row pairs: row (y, z) of primary
+// modes and its conjugate-structured twin row (N-y, N-z) (reference
+// src/zeldovich.cpp:447-466).  Phase 1: the CTA draws the R*N primary modes of its rows once
+// and keeps their state (D, s0, s1, s2, f) in shared memory.  Phase 2: the na*2*R pencils
+// (na packed arrays x {primary, twin} x R rows) are formed from that state, transformed
+// in registers, and written as whole contiguous rows.  Nothing is read from HBM except
+// the RNG/P(k)/eigenmode tables (L2-resident).
+//   y == 0   : the plane is its own twin (reference :485-503): rows z <= N/2 are canonical;
+//              row (0,0) mixes primary (x <= N/2) and twin (x > N/2) entries, origin = 0
+//   y == N/2 : the Nyquist row is zero (reference :640-650 with src/block_array.cpp:487-491)
+template <int N, int NP>
+__global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
+   gen_xfft_kernel(GenParams g, cplx *__restrict__ cube, const cplx *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int M  = N / 16;
+    constexpr int NT = NP * M;
+    cplx *S          = reinterpret_cast<cplx *>(smem_raw);
+    double *state    = reinterpret_cast<double *>(smem_raw + (size_t) NP * FftPlan<N>::PSTRIDE * sizeof(cplx));
+    const int na = g.na;
+    const int tid = threadIdx.x, p = tid % NP, b = tid / NP;
+    const int y = blockIdx.y;  // 0 .. N/2
+    const int z = blockIdx.x;
+    constexpr int half = N / 2;
+    if (y == 0 && z > half) return;  // produced as the twin row of (0, N-z)
+
+    // ---- phase 1: draw the primary modes of row (y, z) once ----
+    for (int x = tid; x < N; x += NT) {
+        Mode m;
+        m.Dr = m.Di = m.s0 = m.s1 = m.s2 = m.f = 0.0;
+        if (y < half) primary_mode(g, x, y, z, m);
+        state[0 * N + x] = m.Dr;
+        state[1 * N + x] = m.Di;
+        state[2 * N + x] = m.s0;
+        state[3 * N + x] = m.s1;
+        state[4 * N + x] = m.s2;
+        state[5 * N + x] = m.f;
+    }
+    __syncthreads();
+
+    // ---- phase 2: the 2*na pencils (na arrays x {row, twin row}), NP at a time ----
+    const bool origin_row = (y == 0 && z == 0);
+    const bool has_twin   = (y > 0 && y < half) || (y == 0 && z > 0 && z < half);
+    const int zh = (N - z) % N, yh = (N - y) % N;
+    const int rounds = 2 * na / NP;
+    for (int rnd = 0; rnd < rounds; rnd++) {
+        const int P = rnd * NP + p, a = P % na, side = P / na;
+        // Every packed entry is a fixed real-linear form of (Dr, Di) (reference
+        // src/zeldovich.cpp:432-434, :447-466 with F,G,H = i s_c D):
+        //   re =      base*Dr - sgn*(c1*Dr)*F - (c2*Di)*F
+        //   im = sgn* base*Di -     (c1*Di)*F + sgn*(c2*Dr)*F
+        // A0: base=1, c1=s0, c2=0, F=1 | A1: base=0, c1=s2, c2=s1, F=1 | A2 / A3: the same with
+        // base=0 and F=f; sgn = -1 for the conjugate-structured twin.  The selectors are
+        // per-thread constants, so the element loop is branch-free.
+        const bool odd     = a & 1;
+        const double base  = (a == 0) ? 1.0 : 0.0;
+        const double *pc1  = state + (odd ? 4 : 2) * N;
+        const double *pc2  = state + 3 * N;
+        const double *pF   = state + 5 * N;
+        const bool useF    = a >= 2;
+        cplx v[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int x = b + M * e;
+            int mx;
+            bool twin;
+            if (side == 0) {
+                twin = origin_row && x > half;  // second half of the (0,0) row comes from the twin
+                mx   = twin ? N - x : x;
+            } else {
+                twin = true;
+                mx   = (N - x) % N;
+            }
+            const double sgn = twin ? -1.0 : 1.0;
+            const double Dr = state[mx], Di = state[N + mx];
+            const double c1 = pc1[mx];
+            const double c2 = odd ? pc2[mx] : 0.0;
+            const double F  = useF ? pF[mx] : 1.0;
+            cplx val;
+            val.x = base * Dr - sgn * ((c1 * Dr) * F) - (c2 * Di) * F;
+            val.y = sgn * (base * Di) - (c1 * Di) * F + sgn * ((c2 * Dr) * F);
+            if (origin_row && side == 0 && x == 0) val = make_double2(0.0, 0.0);
+            v[e] = val;
+        }
+        fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+        const bool live = (side == 0) || has_twin;
+        const long long row = (side == 0) ? ((long long) a * N + z) * N * (long long) N + (long long) y * N
+                                           : ((long long) a * N + zh) * N * (long long) N + (long long) yh * N;
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) st_stream(&cube[row + b + M * e], v[e]);
+        }
+        if (rnd + 1 < rounds) __syncthreads();  // the exchange buffer is reused by the next round
+    }
 }
 
 // byte offsets inside one record, per ICFormat (reference include/output.h:19-42)
@@ -54,102 +182,120 @@ __device__ __forceinline__ void put(unsigned char *rec, int off, double val, int
         *reinterpret_cast<float *>(rec + off) = (float) val;
 }
 
-__device__ __forceinline__ void track(double v, double &mp, double &mn) {
-    if (v > mp) mp = v;
-    if (-v > mn) mn = -v;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
-template <int N, int T>
-__global__ void __launch_bounds__(T *(N / 16))
-   fft_emit_kernel(const cplx *__restrict__ cube, long long z_first, EmitParams ep, const cplx *__restrict__ tw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_var;
-    __shared__ unsigned long long s_max[6];
-    cplx *S         = reinterpret_cast<cplx *>(smem_raw);
-    constexpr int M = N / 16;
-    const int tid = threadIdx.x, p = tid % T, b = tid / T;
-    const int na = ep.na, RT = T / na;
-    const int a = p % na, r = p / na;
-    const long long z = z_first + blockIdx.y;
-    const int y       = blockIdx.x * RT + r;
-    const long long base = (long long) a * N * N * N + (z * N + y) * (long long) N;
-    if (tid == 0) s_var = 0.0;
-    if (tid < 6) s_max[tid] = 0ull;
-    cplx v[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = cube[base + b + M * e];
-    fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
-    __syncthreads();  // the pencil images are dead; reuse shared memory for the record image
-
-    const RecLayout L  = rec_layout(ep.icformat);
-    const int rb       = ep.record_bytes;
-    unsigned char *img = smem_raw + (size_t) r * N * rb;
-    double var = 0.0, mp0 = 0.0, mn0 = 0.0, mp1 = 0.0, mn1 = 0.0;
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const int x        = b + M * e;
-        unsigned char *rec = img + (size_t) x * rb;
-        const double re = v[e].x, im = v[e].y;
-        if (a == 0) {
-            // A0: Re = density, Im = pos[0] -> displ[2]
-            if (L.off_ijk >= 0) {
-                ushort4 id = make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
-                *reinterpret_cast<ushort4 *>(rec + L.off_ijk) = id;
-            }
-            put(rec, L.off_d[2], im, L.dbl);
-            if (!ep.qPLT) put(rec, L.off_v[2], im * ep.vnorm, L.dbl);
-            var += re * re;
-            track(im, mp0, mn0);
-        } else if (a == 1) {
-            // A1: Re = pos[1] -> displ[1], Im = pos[2] -> displ[0]
-            put(rec, L.off_d[1], re, L.dbl);
-            put(rec, L.off_d[0], im, L.dbl);
-            if (!ep.qPLT) {
-                put(rec, L.off_v[1], re * ep.vnorm, L.dbl);
-                put(rec, L.off_v[0], im * ep.vnorm, L.dbl);
-            }
-            track(re, mp0, mn0);
-            track(im, mp1, mn1);
-        } else if (a == 2) {
-            // A2: Im = vel[0] -> vel[2]
-            put(rec, L.off_v[2], im, L.dbl);
-        } else {
-            // A3: Re = vel[1] -> vel[1], Im = vel[2] -> vel[0]
-            put(rec, L.off_v[1], re, L.dbl);
-            put(rec, L.off_v[0], im, L.dbl);
-        }
-    }
-    // statistics: shared-memory atomics, then one global atomic per CTA and quantity
+// Which record field each lane fills.  Array a of the packed set carries
+// (reference src/output.cpp:95-108): A0 = dens + i pos[0], A1 = pos[1] + i pos[2],
+// A2 = . + i vel[0], A3 = vel[1] + i vel[2]; records store displ = (pos[2], pos[1], pos[0])
+// and vel = (vel[2], vel[1], vel[0]) (reference src/output.cpp:128-155).  Without qPLT the
+// velocity is pos * vnorm, written by the lane that owns that pos component.
+struct LaneFields {
+    int o_re, o_im;    // record offsets for Re / Im of this lane's array (-1: not stored)
+    int o_vre, o_vim;  // offsets for Re*vnorm / Im*vnorm (ZA velocities)
+    int o_ijk;         // lane 0 also writes the particle id
+    int s_re, s_im;    // statistics slot (0..2 = pos component) of Re / Im, -1: none
+};
+__device__ __forceinline__ LaneFields lane_fields(int a, const RecLayout &L, int qPLT) {
+    LaneFields f = {-1, -1, -1, -1, -1, -1, -1};
     if (a == 0) {
-        atomicAdd(&s_var, var);
-        atomicMax(&s_max[0], (unsigned long long) __double_as_longlong(mp0));
-        atomicMax(&s_max[3], (unsigned long long) __double_as_longlong(mn0));
+        f.o_ijk = L.off_ijk;
+        f.o_im  = L.off_d[2];
+        f.s_im  = 0;
+        if (!qPLT) f.o_vim = L.off_v[2];
     } else if (a == 1) {
-        atomicMax(&s_max[1], (unsigned long long) __double_as_longlong(mp0));
-        atomicMax(&s_max[4], (unsigned long long) __double_as_longlong(mn0));
-        atomicMax(&s_max[2], (unsigned long long) __double_as_longlong(mp1));
-        atomicMax(&s_max[5], (unsigned long long) __double_as_longlong(mn1));
+        f.o_re = L.off_d[1];
+        f.o_im = L.off_d[0];
+        f.s_re = 1;
+        f.s_im = 2;
+        if (!qPLT) f.o_vre = L.off_v[1], f.o_vim = L.off_v[0];
+    } else if (a == 2) {
+        f.o_im = L.off_v[2];
+    } else {
+        f.o_re = L.off_v[1];
+        f.o_im = L.off_v[0];
+    }
+    return f;
+}
+
+// Record emission from the fully transformed cube (reference WriteParticlesSlab,
+// src/output.cpp:41-234): one thread per particle, records staged in shared memory and
+// copied out with 128-bit stores.
+__global__ void __launch_bounds__(256) emit_kernel(const cplx *__restrict__ cube, int N, long long z_first, EmitParams ep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[8][8];
+    const int tid = threadIdx.x;
+    const long long z = z_first + blockIdx.y;
+    const long long i0 = (long long) blockIdx.x * 256;  // first particle of this block within the plane
+    const long long i  = i0 + tid;                      // y*N + x
+    const int y = (int) (i / N), x = (int) (i % N);
+    const long long N3 = (long long) N * N * N;
+    const long long idx = z * N * (long long) N + i;
+    const RecLayout L = rec_layout(ep.icformat);
+    const int rb = ep.record_bytes, dbl = L.dbl;
+    unsigned char *rec = smem_raw + (size_t) tid * rb;
+    const cplx a0 = ld_stream(&cube[idx]), a1 = ld_stream(&cube[N3 + idx]);
+    const double dens = a0.x;
+    const double pos0 = a0.y, pos1 = a1.x, pos2 = a1.y;
+    double vel0, vel1, vel2;
+    if (ep.qPLT) {
+        const cplx a2 = ld_stream(&cube[2 * N3 + idx]), a3 = ld_stream(&cube[3 * N3 + idx]);
+        vel0 = a2.y, vel1 = a3.x, vel2 = a3.y;
+    } else {
+        vel0 = pos0 * ep.vnorm, vel1 = pos1 * ep.vnorm, vel2 = pos2 * ep.vnorm;
+    }
+    if (L.off_ijk >= 0)
+        *reinterpret_cast<ushort4 *>(rec + L.off_ijk) = make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
+    put(rec, L.off_d[0], pos2, dbl);
+    put(rec, L.off_d[1], pos1, dbl);
+    put(rec, L.off_d[2], pos0, dbl);
+    put(rec, L.off_v[0], vel2, dbl);
+    put(rec, L.off_v[1], vel1, dbl);
+    put(rec, L.off_v[2], vel0, dbl);
+    double q[7] = {dens * dens, fmax(pos0, 0.0), fmax(pos1, 0.0), fmax(pos2, 0.0), fmax(-pos0, 0.0), fmax(-pos1, 0.0), fmax(-pos2, 0.0)};
+    q[0] = warp_sum(q[0]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) q[k] = warp_max(q[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) s_red[tid >> 5][k] = q[k];
     }
     __syncthreads();
-    // coalesced copy-out of RT consecutive rows of records
     {
-        const size_t bytes = (size_t) RT * N * rb;
-        unsigned char *dst = ep.out + ((size_t) ((z - ep.z0) * N + (long long) blockIdx.x * RT) * N) * rb;
-        const int4 *s4     = reinterpret_cast<const int4 *>(smem_raw);
-        int4 *d4           = reinterpret_cast<int4 *>(dst);
-        for (size_t i = tid; i < bytes / 16; i += blockDim.x) d4[i] = s4[i];
+        const size_t bytes = (size_t) 256 * rb;
+        unsigned char *dst = ep.out + ((size_t) ((z - ep.z0) * N * (long long) N + i0)) * rb;
+        const int4 *s4 = reinterpret_cast<const int4 *>(smem_raw);
+        int4 *d4       = reinterpret_cast<int4 *>(dst);
+        for (size_t k = tid; k < bytes / 16; k += 256) __stcs(&d4[k], s4[k]);
     }
     if (tid < 7) {
+        double acc = s_red[0][tid];
+        for (int w = 1; w < 8; w++) acc = (tid == 0) ? acc + s_red[w][tid] : fmax(acc, s_red[w][tid]);
         double *slot = ep.stats + 8 * ((blockIdx.x + blockIdx.y * gridDim.x) % ZPLT_STAT_SLOTS);
         if (tid == 0)
-            atomicAdd(&slot[0], s_var);
+            atomicAdd(&slot[0], acc);
         else
-            atomicMax(reinterpret_cast<unsigned long long *>(&slot[tid]), s_max[tid - 1]);
+            atomicMax(reinterpret_cast<unsigned long long *>(&slot[tid]), (unsigned long long) __double_as_longlong(acc));
     }
 }
 
 // ------------------------------------------------------------------ dispatch -------
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+// pencils per CTA for the in-place strided/row passes
 int fft_tile_T(int N) {
+    int t = env_int("ZPLT_TILE_T", 0);
+    if (t) return t;
     switch (N) {
         case 16: return 16;
         case 32: return 32;
@@ -169,54 +315,79 @@ static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStr
     size_t smem = fft_tile_smem(N, T);
     cudaError_t e = cudaFuncSetAttribute(fft_tile_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
+    {
+        int cv = env_int("ZPLT_CARVEOUT", -1);
+        if (cv >= 0) cudaFuncSetAttribute(fft_tile_kernel<N, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+    }
     dim3 grid(g.grid_x, g.grid_y, g.grid_z);
     fft_tile_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(data, g, tw);
     return (int) cudaGetLastError();
 }
 
-int launch_fft_tiles(int N, cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
-    switch (N) {
-        case 16: return launch_tiles_t<16, 16>(data, g, tw, st);
-        case 32: return launch_tiles_t<32, 32>(data, g, tw, st);
-        case 64: return launch_tiles_t<64, 32>(data, g, tw, st);
-        case 128: return launch_tiles_t<128, 16>(data, g, tw, st);
-        case 256: return launch_tiles_t<256, 16>(data, g, tw, st);
-        case 512: return launch_tiles_t<512, 8>(data, g, tw, st);
-        case 1024: return launch_tiles_t<1024, 8>(data, g, tw, st);
-        case 2048: return launch_tiles_t<2048, 4>(data, g, tw, st);
-    }
-    return (int) cudaErrorInvalidValue;
-}
-
-template <int N, int T>
-static int launch_emit_t(const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
-                         cudaStream_t st, int *launches) {
-    const int RT   = T / ep.na;
-    size_t smem    = fft_tile_smem(N, T);
-    size_t recs    = (size_t) RT * N * ep.record_bytes;
-    if (recs > smem) smem = recs;
-    cudaError_t e = cudaFuncSetAttribute(fft_emit_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+template <int N, int NP>
+static int launch_genx_t(const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st) {
+    if ((2 * g.na) % NP) return (int) cudaErrorInvalidValue;
+    size_t smem = fft_tile_smem(N, NP) + (size_t) 6 * N * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(gen_xfft_kernel<N, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    // grid.y is limited to 65535: fine for nz <= 2048
-    dim3 grid(N / RT, (unsigned) nz, 1);
-    fft_emit_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(cube, z_first, ep, tw);
-    if (launches) *launches += 1;
+    dim3 grid(N, N / 2 + 1, 1);
+    gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, cube, tw);
     return (int) cudaGetLastError();
 }
 
-int launch_fft_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
-                    cudaStream_t st, int *launches) {
+#define ZPLT_CASE(FN, NN, TT, ...) \
+    if (N == NN && T == TT) return FN<NN, TT>(__VA_ARGS__);
+
+// pencils transformed concurrently by one CTA of the generation + x-FFT kernel (divides 2*narray)
+int gen_xfft_T(int N, int na) {
+    int t = env_int("ZPLT_GENX_T", 0);
+    if (t) return t;
     switch (N) {
-        case 16: return launch_emit_t<16, 16>(cube, z_first, nz, ep, tw, st, launches);
-        case 32: return launch_emit_t<32, 32>(cube, z_first, nz, ep, tw, st, launches);
-        case 64: return launch_emit_t<64, 32>(cube, z_first, nz, ep, tw, st, launches);
-        case 128: return launch_emit_t<128, 16>(cube, z_first, nz, ep, tw, st, launches);
-        case 256: return launch_emit_t<256, 16>(cube, z_first, nz, ep, tw, st, launches);
-        case 512: return launch_emit_t<512, 8>(cube, z_first, nz, ep, tw, st, launches);
-        case 1024: return launch_emit_t<1024, 8>(cube, z_first, nz, ep, tw, st, launches);
-        case 2048: return launch_emit_t<2048, 4>(cube, z_first, nz, ep, tw, st, launches);
+        case 512: return na == 4 ? 8 : 4;
+        case 2048: return 2;
+        default: return 4;
     }
+}
+
+int launch_gen_xfft(int N, int T, const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st) {
+    ZPLT_CASE(launch_genx_t, 16, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 32, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 64, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 128, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 256, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 512, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 512, 8, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 1024, 8, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 1024, 4, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 1024, 2, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 2048, 2, g, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 2048, 4, g, cube, tw, st)
     return (int) cudaErrorInvalidValue;
+}
+
+int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
+    ZPLT_CASE(launch_tiles_t, 16, 16, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 32, 32, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 64, 32, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 128, 16, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 256, 16, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 256, 8, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 512, 8, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 512, 4, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 1024, 8, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 1024, 4, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 1024, 2, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 2048, 4, data, g, tw, st)
+    ZPLT_CASE(launch_tiles_t, 2048, 2, data, g, tw, st)
+    return (int) cudaErrorInvalidValue;
+}
+
+int launch_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st, int *launches) {
+    if (((long long) N * N) % 256) return (int) cudaErrorInvalidValue;
+    dim3 grid((unsigned) ((long long) N * N / 256), (unsigned) nz, 1);
+    emit_kernel<<<grid, 256, 256 * ep.record_bytes, st>>>(cube, N, z_first, ep);
+    if (launches) *launches += 1;
+    return (int) cudaGetLastError();
 }
 
 }  // namespace zplt

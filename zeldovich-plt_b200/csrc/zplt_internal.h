@@ -32,12 +32,14 @@ struct EmitParams {
 #define ZPLT_STAT_SLOTS 64
 
 int fft_tile_T(int N);            // pencils per CTA used for length N (strided / row kernels)
+int gen_xfft_T(int N, int na);    // pencils per CTA of the generation + x-FFT kernel
 size_t fft_tile_smem(int N, int T);
-// In-place backward FFT of every pencil described by geom.  Returns cudaError_t.
-int launch_fft_tiles(int N, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
-// x-axis FFT of rows + record emission for planes [z0, z0+nz) of a [na][N][N][N] cube.
-int launch_fft_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
-                    cudaStream_t st, int *launches);
+// Fused mode generation + x-axis FFT, writes the whole [na][z][y][x] cube.
+int launch_gen_xfft(int N, int T, const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st);
+// In-place backward FFT of every pencil described by geom (tiles of T pencils).  Returns cudaError_t.
+int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+// Record emission for planes [z_first, z_first+nz) of a fully transformed [na][N][N][N] cube.
+int launch_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st, int *launches);
 
 int launch_power_table(double *ptab, long long count, double fundamental2, int is_powerlaw, double index, int n,
                        const double *x, const double *y, const double *y2, double normalization, double smooth2,
