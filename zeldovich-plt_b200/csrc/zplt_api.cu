@@ -391,10 +391,7 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
         c->launches[1] = 1;
     }
     CK(cudaEventRecord(c->ev_gen[2], c->stream));
-    if (with_fft) {
-        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 1), c->tw, c->stream));
-        c->launches[2] = 1;
-    }
+    // the y axis is transformed inside the emission kernel (zplt_emit_planes)
     CK(cudaEventRecord(c->ev_gen[3], c->stream));
     c->n_emit_ev = 0;
     c->generated = with_fft;
@@ -419,7 +416,7 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
     ep.stats        = c->stats;
     bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
     if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
-    CK(launch_emit(c->N, c->cube, z0, nz, ep, c->stream, &c->launches[3]));
+    CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->cube, z0, nz, ep, c->tw, c->stream, &c->launches[3]));
     if (timed) {
         CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev + 1], c->stream));
         c->n_emit_ev++;

@@ -226,6 +226,174 @@ __device__ __forceinline__ LaneFields lane_fields(int a, const RecLayout &L, int
     return f;
 }
 
+// ------------------------------------------------------------------ y FFT + emission
+// Last axis (y, stride N) fused with particle emission (reference WriteParticlesSlab,
+// src/output.cpp:41-234).  A CTA owns the tile (z, all y, T consecutive x) and walks the
+// packed arrays one after the other — the array index is uniform across the CTA, so the
+// per-array record logic has no divergence.  Nothing is written back to the cube: the
+// transformed values go straight from registers into the records.
+//   RVZel (the headline format): the 32-byte record is written as two aligned 16-byte
+//   halves, [i j k pad | displ0 displ1] from A1 alone and [displ2 | vel0 vel1 vel2] from
+//   A0/A3/A2, with the two floats that must wait (Im A0, Im A2) parked in shared memory.
+//   Other formats: each field is stored as soon as its array has been transformed.
+// Reduce three per-thread partials over the warp and leave them in s_red[warp][slot]
+// (slot 0 is a sum, every other slot a maximum; slot 7 is scratch).
+template <int NT>
+__device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q0, int s0, double q1, int s1, double q2, int s2) {
+    if constexpr (NT >= 32) {
+        q0 = (s0 == 0) ? warp_sum(q0) : warp_max(q0);
+        q1 = warp_max(q1);
+        q2 = warp_max(q2);
+        if ((tid & 31) == 0) s_red[tid >> 5][s0] = q0, s_red[tid >> 5][s1] = q1, s_red[tid >> 5][s2] = q2;
+    } else {
+        s_red[tid][s0] = q0, s_red[tid][s1] = q1, s_red[tid][s2] = q2;
+    }
+}
+
+// One packed array A of the tile: load, transform along y, then either park its values or
+// complete record fields.  A is a compile-time constant, the format test is CTA-uniform and
+// sits outside the element loops.
+template <int N, int T, int A>
+__device__ __forceinline__ void emit_array(const cplx *__restrict__ src, cplx *S, float *keep, const cplx *__restrict__ tw,
+                                           const EmitParams &ep, const RecLayout &L, unsigned char *rec0, long long z, int x,
+                                           int tid, int p, int b, bool first, double (*s_red)[8]) {
+    constexpr int M  = N / 16;
+    constexpr int NT = T * M;
+    const int rb = ep.record_bytes, dbl = L.dbl;
+    const bool rvzel = ep.icformat == 1, qplt = ep.qPLT;
+    const double vn = ep.vnorm;
+    cplx v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = ld_stream(&src[(long long) (b + M * e) * N]);
+    if (!first) __syncthreads();  // the previous array's last exchange read is complete
+    fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+    if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]
+        {
+            double var = 0.0, mp = 0.0, mn = 0.0;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                var += v[e].x * v[e].x;
+                mp = fmax(mp, v[e].y), mn = fmax(mn, -v[e].y);
+            }
+            fold_stats<NT>(s_red, tid, var, 0, mp, 1, mn, 4);
+        }
+        if (rvzel) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                keep[(0 * 16 + e) * NT + tid] = (float) v[e].y;
+                if (!qplt) keep[(1 * 16 + e) * NT + tid] = (float) (v[e].y * vn);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
+                put(rec, L.off_d[2], v[e].y, dbl);
+                if (!qplt) put(rec, L.off_v[2], v[e].y * vn, dbl);
+            }
+        }
+    } else if (A == 2) {  // Im = vel[0] -> vel[2]
+        if (rvzel) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) keep[(1 * 16 + e) * NT + tid] = (float) v[e].y;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) put(rec0 + (size_t) (b + M * e) * N * rb, L.off_v[2], v[e].y, dbl);
+        }
+    } else if (A == 1) {  // Re = pos[1] -> displ[1], Im = pos[2] -> displ[0]
+        {
+            double mp1 = 0.0, mn1 = 0.0, mp2 = 0.0, mn2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                mp1 = fmax(mp1, v[e].x), mn1 = fmax(mn1, -v[e].x);
+                mp2 = fmax(mp2, v[e].y), mn2 = fmax(mn2, -v[e].y);
+            }
+            fold_stats<NT>(s_red, tid, mp1, 2, mn1, 5, mp2, 3);
+            fold_stats<NT>(s_red, tid, mn2, 6, 0.0, 7, 0.0, 7);
+        }
+        if (rvzel) {
+            const unsigned int w1 = (unsigned int) (unsigned short) x;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int y = b + M * e;
+                unsigned char *rec = rec0 + (size_t) y * N * rb;
+                const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
+                __stcs(reinterpret_cast<float4 *>(rec),
+                       make_float4(__uint_as_float(w0), __uint_as_float(w1), (float) v[e].y, (float) v[e].x));
+                if (!qplt)
+                    __stcs(reinterpret_cast<float4 *>(rec + 16),
+                           make_float4(keep[(0 * 16 + e) * NT + tid], (float) (v[e].y * vn), (float) (v[e].x * vn),
+                                       keep[(1 * 16 + e) * NT + tid]));
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int y = b + M * e;
+                unsigned char *rec = rec0 + (size_t) y * N * rb;
+                if (L.off_ijk >= 0)
+                    *reinterpret_cast<ushort4 *>(rec + L.off_ijk) =
+                       make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
+                put(rec, L.off_d[1], v[e].x, dbl);
+                put(rec, L.off_d[0], v[e].y, dbl);
+                if (!qplt) {
+                    put(rec, L.off_v[1], v[e].x * vn, dbl);
+                    put(rec, L.off_v[0], v[e].y * vn, dbl);
+                }
+            }
+        }
+    } else {  // A == 3: Re = vel[1] -> vel[1], Im = vel[2] -> vel[0]
+        if (rvzel) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
+                __stcs(reinterpret_cast<float4 *>(rec + 16),
+                       make_float4(keep[(0 * 16 + e) * NT + tid], (float) v[e].y, (float) v[e].x,
+                                   keep[(1 * 16 + e) * NT + tid]));
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
+                put(rec, L.off_v[1], v[e].x, dbl);
+                put(rec, L.off_v[0], v[e].y, dbl);
+            }
+        }
+    }
+}
+
+template <int N, int T>
+__global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
+   fft_emit_strided_kernel(const cplx *__restrict__ cube, long long z_first, EmitParams ep, const cplx *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[32][8];
+    constexpr int M  = N / 16;
+    constexpr int NT = T * M;
+    cplx *S      = reinterpret_cast<cplx *>(smem_raw);
+    float *keep  = reinterpret_cast<float *>(smem_raw + (size_t) T * FftPlan<N>::PSTRIDE * sizeof(cplx));  // [2][16][NT]
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    const long long z = z_first + blockIdx.y;
+    const int x       = blockIdx.x * T + p;
+    const long long N3 = (long long) N * N * N;
+    const cplx *src    = cube + z * N * (long long) N + x;  // + a*N3 + y*N
+    const RecLayout L  = rec_layout(ep.icformat);
+    unsigned char *rec0 = ep.out + ((size_t) ((z - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
+    // A0 and A2 first (their values wait in shared memory), then A1 and A3 complete the record halves
+    emit_array<N, T, 0>(src, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
+    if (ep.qPLT) emit_array<N, T, 2>(src + 2 * N3, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    emit_array<N, T, 1>(src + N3, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    if (ep.qPLT) emit_array<N, T, 3>(src + 3 * N3, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    __syncthreads();
+    if (tid < 7) {
+        constexpr int NW = (NT >= 32) ? NT / 32 : NT;
+        double a7 = s_red[0][tid];
+        for (int w = 1; w < NW; w++) a7 = (tid == 0) ? a7 + s_red[w][tid] : fmax(a7, s_red[w][tid]);
+        double *slot = ep.stats + 8 * ((blockIdx.x + blockIdx.y * gridDim.x) % ZPLT_STAT_SLOTS);
+        if (tid == 0)
+            atomicAdd(&slot[0], a7);
+        else
+            atomicMax(reinterpret_cast<unsigned long long *>(&slot[tid]), (unsigned long long) __double_as_longlong(a7));
+    }
+}
+
 // Record emission from the fully transformed cube (reference WriteParticlesSlab,
 // src/output.cpp:41-234): one thread per particle, records staged in shared memory and
 // copied out with 128-bit stores.
@@ -379,6 +547,36 @@ int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &g, const cplx *tw
     ZPLT_CASE(launch_tiles_t, 1024, 2, data, g, tw, st)
     ZPLT_CASE(launch_tiles_t, 2048, 4, data, g, tw, st)
     ZPLT_CASE(launch_tiles_t, 2048, 2, data, g, tw, st)
+    return (int) cudaErrorInvalidValue;
+}
+
+template <int N, int T>
+static int launch_emit_strided_t(const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
+                                 cudaStream_t st, int *launches) {
+    size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    dim3 grid(N / T, (unsigned) nz, 1);
+    fft_emit_strided_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(cube, z_first, ep, tw);
+    if (launches) *launches += 1;
+    return (int) cudaGetLastError();
+}
+
+// y-axis FFT + record emission for planes [z_first, z_first+nz); the cube holds the x- and z-transformed arrays
+int launch_fft_emit_strided(int N, int T, const cplx *cube, long long z_first, long long nz, const EmitParams &ep,
+                            const cplx *tw, cudaStream_t st, int *launches) {
+    ZPLT_CASE(launch_emit_strided_t, 16, 16, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 32, 32, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 64, 32, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 128, 16, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 256, 16, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 256, 8, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 512, 8, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 512, 4, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 1024, 4, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 2048, 2, cube, z_first, nz, ep, tw, st, launches)
     return (int) cudaErrorInvalidValue;
 }
 

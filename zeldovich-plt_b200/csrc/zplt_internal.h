@@ -38,6 +38,9 @@ size_t fft_tile_smem(int N, int T);
 int launch_gen_xfft(int N, int T, const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st);
 // In-place backward FFT of every pencil described by geom (tiles of T pencils).  Returns cudaError_t.
 int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+// y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
+int launch_fft_emit_strided(int N, int T, const cplx *cube, long long z_first, long long nz, const EmitParams &ep,
+                            const cplx *tw, cudaStream_t st, int *launches);
 // Record emission for planes [z_first, z_first+nz) of a fully transformed [na][N][N][N] cube.
 int launch_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st, int *launches);
 
