@@ -89,7 +89,8 @@ int zplt_set_power_law(zplt_ctx *ctx, double index, double normalization, double
 int zplt_set_eigenmodes(zplt_ctx *ctx, int32_t ppd_e, const double *table);
 
 /* ---- device resources ---------------------------------------------------------- */
-/* Bytes of device workspace the context needs (spectral slabs + tables). */
+/* Bytes of device workspace the context needs: narray*ppd^3/nranks complex doubles, twice that
+ * (send + receive buffer) when nranks > 1. */
 size_t zplt_workspace_bytes(const zplt_ctx *ctx);
 /* Optional: hand the context a caller-owned device buffer (e.g. a torch tensor's
  * data_ptr) of at least zplt_workspace_bytes(); otherwise it cudaMallocs its own. */
@@ -110,6 +111,24 @@ int zplt_emit_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *device_out);
 /* Convenience for host callers: emit planes z0..z0+nz-1 and copy them to `host_out`
  * (pageable or pinned), double-buffered through an internal staging ring.  Synchronous. */
 int zplt_fetch_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *host_out);
+/* ---- slab decomposition (nranks > 1): one context per GPU, one exchange ----------
+ * zplt_generate() then runs stage 1 (generation, x and z transforms) on this rank's 2*ppd/(2*nranks)
+ * rows and leaves them in the send buffer as nranks contiguous blocks of `bytes_per_peer`
+ * bytes, block r = the planes rank r owns.  The CALLER performs the all-to-all (block r of
+ * every rank to rank r, received in rank order into `recv`: NCCL all_to_all_single or peer
+ * copies) — the y<->z transpose the reference does through BlockArray::StoreBlock/LoadBlock
+ * (reference src/block_array.cpp:387-414, 466-504) — and then calls zplt_exchange_done().
+ * After that zplt_emit_planes / zplt_fetch_planes address this rank's ppd/nranks planes by
+ * LOCAL index (global z = rank*ppd/nranks + local); particle ids carry the global index. */
+int zplt_exchange_info(zplt_ctx *ctx, void **send, void **recv, size_t *bytes_per_peer);
+int zplt_exchange_done(zplt_ctx *ctx);
+/* Layout of the decomposition (host mirror of the device index math, for tests and bindings):
+ * which rank owns row y in stage 1 and in which of its slots. */
+int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32_t *slot);
+/* Offset, in complex elements, of x-row (a, z, y) inside rank `rank`'s send buffer (stage 1) or
+ * receive buffer (stage 2); -1 if that rank does not hold it. */
+int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray, int32_t stage, int32_t rank, int32_t a, int64_t z, int64_t y);
+
 /* Reset the statistics accumulated by the emit calls. */
 int zplt_reset_stats(zplt_ctx *ctx);
 /* density_variance = sum over emitted particles of dens^2; max_disp[j] = signed value of

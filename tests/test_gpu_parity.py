@@ -26,7 +26,7 @@ def pkg():
     return load_package()
 
 
-def make_ctx(pkg, kw, pk, eig):
+def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
     """Product context from keyword parameters; the spline comes from the product's own host code."""
     synth = load_synth()
     tmp = tempfile.mkdtemp(prefix="zplt_")
@@ -53,7 +53,9 @@ def make_ctx(pkg, kw, pk, eig):
     synth.write_param(os.path.join(tmp, "c.par"), **over)
     P = pkg.Parameters(os.path.join(tmp, "c.par"))
     power = pkg.PowerSpectrum(P)
-    ctx = pkg.Context(P.config(device=0))
+    cfg = P.config(device=0)
+    cfg.rank, cfg.nranks = rank, nranks
+    ctx = pkg.Context(cfg)
     power.apply(ctx)
     if eig is not None:
         ctx.load_eigenmodes_file(P.PLT_filename)
@@ -281,3 +283,51 @@ def test_errors_are_reported(pkg):
     with pytest.raises(pkg.ZpltError):
         ctx.generate()  # power spectrum not set
     ctx.close()
+
+
+# ---------------------------------------------------------------- slab decomposition
+@pytest.mark.parametrize("G,case", [
+    (2, dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16)),
+    (4, dict(ppd=64, icformat="RVZel")),
+    (8, dict(ppd=128, qPLT=1, icformat="RVZel", eig=128)),
+])
+def test_slab_decomposition_single_process(pkg, oracle, G, case):
+    """All G ranks of a slab-decomposed run emulated on one GPU (device copies stand in for the all-to-all):
+    the concatenated planes must equal the oracle's records."""
+    import torch
+
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    N = kw["ppd"]
+    ctxs, bufs = [], []
+    for r in range(G):
+        ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig, rank=r, nranks=G)
+        buf = torch.empty(ctx.workspace_bytes() // 8, dtype=torch.float64, device="cuda:0")
+        ctx.set_workspace(buf.data_ptr(), buf.numel() * 8)
+        ctx.generate()
+        ctx.synchronize()
+        ctxs.append(ctx)
+        bufs.append(buf)
+    half = bufs[0].numel() // 2
+    blk = half // G
+    for dst in range(G):
+        for src in range(G):
+            bufs[dst][half + src * blk: half + (src + 1) * blk] = bufs[src][dst * blk:(dst + 1) * blk]
+    torch.cuda.synchronize()
+    parts = []
+    var, md = 0.0, np.zeros(3)
+    for r in range(G):
+        ctxs[r].exchange_done()
+        parts.append(ctxs[r].fetch_planes(0, N // G))
+        st = ctxs[r].stats()
+        var += st["density_variance"]
+        md = np.where(np.abs(st["max_disp"]) > np.abs(md), st["max_disp"], md)
+        ctxs[r].close()
+    got = np.concatenate(parts)
+    want, wst = oracle.run(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    compare_records(oracle, got, want)
+    assert abs(var / wst["density_variance"] - 1) < 1e-10
+    assert np.allclose(md, wst["max_disp"], rtol=1e-10)

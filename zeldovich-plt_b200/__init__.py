@@ -89,7 +89,7 @@ EXPORTS = [
     "zplt_create", "zplt_destroy", "zplt_last_error", "zplt_record_bytes", "zplt_narray", "zplt_set_power_spline",
     "zplt_set_power_law", "zplt_set_eigenmodes", "zplt_workspace_bytes", "zplt_set_workspace", "zplt_set_stream",
     "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
-    "zplt_get_timings", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
+    "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
     "zplt_power_sigmaR", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
@@ -128,6 +128,11 @@ def lib():
     L.zplt_get_stats.argtypes = [vp, dp, dp]
     L.zplt_synchronize.argtypes = [vp]
     L.zplt_get_timings.argtypes = [vp, dp]
+    L.zplt_exchange_info.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.zplt_exchange_done.argtypes = [vp]
+    L.zplt_slab_owner.argtypes = [i64, i32, i64, C.POINTER(i32), C.POINTER(i32)]
+    L.zplt_slab_offset.argtypes = [i64, i32, i32, i32, i32, i32, i64, i64]
+    L.zplt_slab_offset.restype = i64
     L.zplt_dbg_pcg_draws.argtypes = [u64, u64, u64, i64, C.POINTER(u64)]
     L.zplt_dbg_mode_draws.argtypes = [vp, i64, C.POINTER(i32), C.POINTER(u64), dp]
     L.zplt_dbg_power_table.argtypes = [vp, i64, dp]
@@ -310,6 +315,15 @@ class Context:
     def fetch_planes_ptr(self, z0, nz, host_ptr):
         _ck(lib().zplt_fetch_planes(self._h, z0, nz, C.c_void_p(host_ptr)))
 
+    def exchange_info(self):
+        """(send_ptr, recv_ptr, bytes_per_peer) of a slab-decomposed context."""
+        send, recv, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _ck(lib().zplt_exchange_info(self._h, C.byref(send), C.byref(recv), C.byref(nb)))
+        return send.value, recv.value, nb.value
+
+    def exchange_done(self):
+        _ck(lib().zplt_exchange_done(self._h))
+
     def reset_stats(self):
         _ck(lib().zplt_reset_stats(self._h))
 
@@ -355,6 +369,16 @@ class Context:
         out = np.zeros((self.narray, N, N, N), dtype=np.complex128)
         _ck(lib().zplt_dbg_after_generate(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+
+def slab_owner(ppd, nranks, y):
+    r, s = C.c_int32(), C.c_int32()
+    _ck(lib().zplt_slab_owner(ppd, nranks, y, C.byref(r), C.byref(s)))
+    return r.value, s.value
+
+
+def slab_offset(ppd, nranks, narray, stage, rank, a, z, y):
+    return lib().zplt_slab_offset(ppd, nranks, narray, stage, rank, a, z, y)
 
 
 def pcg_draws(seed, offset, n):

@@ -73,6 +73,9 @@ struct zplt_ctx {
     zplt_config cfg;
     int N, na, device;
     GenParams gp;
+    SlabGeom sg;
+    size_t slab_elems;  // complex elements of one slab buffer
+    bool exchanged;
     double vnorm;
     cudaStream_t stream, copy_stream;
     bool own_stream;
@@ -133,7 +136,9 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     if (zplt_record_bytes(cfg->icformat) == 0) return fail(ZPLT_EINVAL, "unknown ICFormat code %d", cfg->icformat);
     if (cfg->qPLT && !(cfg->icformat == ZPLT_FMT_RVZEL || cfg->icformat == ZPLT_FMT_RVDOUBLEZEL))
         return fail(ZPLT_EINVAL, "ZD_qPLT requires an RV* ICFormat (reference src/parameters.cpp:169)");
-    if (cfg->nranks != 1 || cfg->rank != 0) return fail(ZPLT_EINVAL, "slab decomposition (nranks>1) is not built yet");
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(ZPLT_EINVAL, "bad rank %d of %d", cfg->rank, cfg->nranks);
+    if (cfg->nranks > 1 && ((N / 2) % cfg->nranks || N / (2 * cfg->nranks) < 1))
+        return fail(ZPLT_EINVAL, "nranks=%d must divide ppd/2=%lld", cfg->nranks, N / 2);
 
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
@@ -161,7 +166,10 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
         CK(cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->stage_full[i], cudaEventDisableTiming));
     }
-    c->cube_bytes = (size_t) c->na * N * N * N * sizeof(cplx);
+    c->sg.N = (int) N, c->sg.G = cfg->nranks, c->sg.rank = cfg->rank, c->sg.h = (int) (N / (2 * cfg->nranks)), c->sg.na = c->na;
+    c->slab_elems = (size_t) c->na * N * N * N / cfg->nranks;
+    // one buffer on a single GPU; stage-1 + stage-2 buffers when the grid is slab-decomposed
+    c->cube_bytes = c->slab_elems * sizeof(cplx) * (cfg->nranks > 1 ? 2 : 1);
 
     // derived scalars, written exactly as the reference computes them
     GenParams &g  = c->gp;
@@ -371,13 +379,16 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
     int rc = ready(c);
     if (rc) return rc;
     c->launches[0] = c->launches[1] = c->launches[2] = c->launches[3] = 0;
+    const bool slab = c->sg.G > 1;
+    if (slab && !with_fft) return fail(ZPLT_EINVAL, "spectral introspection is single-GPU only");
     CK(cudaEventRecord(c->ev_gen[0], c->stream));
     const int gt = with_fft ? gen_xfft_T(c->N, c->na) : 0;
     if (gt) {
         // fused: draw the modes and transform the x axis in one kernel
-        CK(launch_gen_xfft(c->N, gt, c->gp, c->cube, c->tw, c->stream));
+        CK(launch_gen_xfft(c->N, gt, c->gp, c->sg, c->cube, c->tw, c->stream));
         c->launches[0] = 1;
     } else {
+        if (slab) return fail(ZPLT_EINVAL, "no fused generation kernel for this size");
         CK(launch_generate(c->gp, c->cube, c->stream));
         c->launches[0] = 1;
         if (with_fft) {
@@ -387,7 +398,16 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
     }
     CK(cudaEventRecord(c->ev_gen[1], c->stream));
     if (with_fft) {
-        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 2), c->tw, c->stream));
+        TileGeom g = geom_axis(c->N, c->na, 2);
+        if (slab) {
+            // stage-1 buffer B1[z][a][slot][x]: pencils along z for each of the na*2h local rows
+            const int T = fft_tile_T(c->N);
+            g.astride = 0, g.grid_z = 1;
+            g.ostride = c->N, g.grid_y = c->na * 2 * c->sg.h;
+            g.tstride = T, g.grid_x = c->N / T, g.pa = T, g.plo_stride = 1, g.phi_stride = 0;
+            g.nstride = (long long) c->na * 2 * c->sg.h * c->N;
+        }
+        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->stream));
         c->launches[1] = 1;
     }
     CK(cudaEventRecord(c->ev_gen[2], c->stream));
@@ -395,6 +415,7 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
     CK(cudaEventRecord(c->ev_gen[3], c->stream));
     c->n_emit_ev = 0;
     c->generated = with_fft;
+    c->exchanged = false;
     return ZPLT_OK;
 }
 
@@ -403,7 +424,9 @@ extern "C" int zplt_generate(zplt_ctx *c) { return run_generate(c, true); }
 extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *device_out) {
     if (!c || !device_out) return fail(ZPLT_EINVAL, "null argument");
     if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
-    if (z0 < 0 || nz <= 0 || z0 + nz > c->N) return fail(ZPLT_EINVAL, "plane range [%lld,%lld) outside [0,%d)", (long long) z0, (long long) (z0 + nz), c->N);
+    const int nplanes = c->N / c->sg.G;  // planes this rank owns (all of them on a single GPU)
+    if (z0 < 0 || nz <= 0 || z0 + nz > nplanes) return fail(ZPLT_EINVAL, "plane range [%lld,%lld) outside [0,%d)", (long long) z0, (long long) (z0 + nz), nplanes);
+    if (c->sg.G > 1 && !c->exchanged) return fail(ZPLT_ESTATE, "the slab exchange has not been run (zplt_exchange_info / zplt_exchange_done)");
     CK(cudaSetDevice(c->device));
     EmitParams ep;
     ep.icformat     = c->cfg.icformat;
@@ -416,7 +439,8 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
     ep.stats        = c->stats;
     bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
     if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
-    CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->cube, z0, nz, ep, c->tw, c->stream, &c->launches[3]));
+    CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->sg.G > 1 ? c->cube + c->slab_elems : c->cube, c->sg, z0, nz, ep, c->tw,
+                               c->stream, &c->launches[3]));
     if (timed) {
         CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev + 1], c->stream));
         c->n_emit_ev++;
@@ -427,7 +451,7 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
 extern "C" int zplt_fetch_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *host_out) {
     if (!c || !host_out) return fail(ZPLT_EINVAL, "null argument");
     if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
-    if (z0 < 0 || nz <= 0 || z0 + nz > c->N) return fail(ZPLT_EINVAL, "plane range outside the lattice");
+    if (z0 < 0 || nz <= 0 || z0 + nz > c->N / c->sg.G) return fail(ZPLT_EINVAL, "plane range outside this rank's planes");
     CK(cudaSetDevice(c->device));
     const size_t plane = (size_t) c->N * c->N * zplt_record_bytes(c->cfg.icformat);
     long long chunk    = (long long) ((256ull << 20) / plane);
@@ -458,6 +482,48 @@ extern "C" int zplt_fetch_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *host
     CK(cudaStreamSynchronize(c->copy_stream));
     CK(cudaStreamSynchronize(c->stream));
     return ZPLT_OK;
+}
+
+extern "C" int zplt_exchange_info(zplt_ctx *c, void **send, void **recv, size_t *bytes_per_peer) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (c->sg.G == 1) return fail(ZPLT_EINVAL, "a single-GPU context has no exchange");
+    int rc = ensure_cube(c);
+    if (rc) return rc;
+    if (send) *send = c->cube;
+    if (recv) *recv = c->cube + c->slab_elems;
+    if (bytes_per_peer) *bytes_per_peer = (size_t) slab_block_elems(c->sg) * sizeof(cplx);
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_exchange_done(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
+    c->exchanged = true;
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32_t *slot) {
+    if (nranks < 1 || ppd < 2 || (ppd / 2) % nranks || y < 0 || y >= ppd || !rank || !slot) return fail(ZPLT_EINVAL, "bad arguments");
+    int r, s;
+    slab_owner((int) ppd, nranks, (int) y, r, s);
+    *rank = r, *slot = s;
+    return ZPLT_OK;
+}
+
+extern "C" int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray, int32_t stage, int32_t rank, int32_t a, int64_t z,
+                                    int64_t y) {
+    SlabGeom g;
+    g.N = (int) ppd, g.G = nranks, g.rank = rank, g.h = (int) (ppd / (2 * nranks)), g.na = narray;
+    if (stage == 1) {  // where rank `rank` (the owner of row y) keeps row (a, z, y) before the exchange
+        int r, s;
+        slab_owner(g.N, g.G, (int) y, r, s);
+        if (r != rank) return -1;
+        return slab_b1_row(g, a, (int) z, s);
+    }
+    // stage 2: where rank `rank` (the owner of plane z) finds row (a, z, y) after the exchange
+    const int np = g.N / g.G;
+    if (z / np != rank) return -1;
+    return slab_b2_row(g, a, (int) (z % np), (int) y);
 }
 
 extern "C" int zplt_reset_stats(zplt_ctx *c) {
@@ -577,6 +643,7 @@ extern "C" int zplt_dbg_spectral(zplt_ctx *c, double *host_out) {
 extern "C" int zplt_dbg_after_generate(zplt_ctx *c, double *host_out) {
     if (!c || !host_out) return fail(ZPLT_EINVAL, "null argument");
     if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
+    if (c->sg.G > 1) return fail(ZPLT_EINVAL, "single-GPU introspection only");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(host_out, c->cube, c->cube_bytes, cudaMemcpyDeviceToHost));

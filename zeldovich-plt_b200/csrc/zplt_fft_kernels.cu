@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_k
 //   y == N/2 : the Nyquist row is zero (reference :640-650 with src/block_array.cpp:487-491)
 template <int N, int NP>
 __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
-   gen_xfft_kernel(GenParams g, cplx *__restrict__ cube, const cplx *__restrict__ tw) {
+   gen_xfft_kernel(GenParams g, SlabGeom sg, cplx *__restrict__ cube, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int M  = N / 16;
     constexpr int NT = NP * M;
@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     double *state    = reinterpret_cast<double *>(smem_raw + (size_t) NP * FftPlan<N>::PSTRIDE * sizeof(cplx));
     const int na = g.na;
     const int tid = threadIdx.x, p = tid % NP, b = tid / NP;
-    const int y = blockIdx.y;  // 0 .. N/2
-    const int z = blockIdx.x;
     constexpr int half = N / 2;
+    // single GPU: y = 0 .. N/2.  Slab rank: its h primary rows, plus the Nyquist row on rank 0.
+    const int y = (sg.G == 1) ? (int) blockIdx.y : ((int) blockIdx.y < sg.h ? sg.rank * sg.h + (int) blockIdx.y : half);
+    const int z = blockIdx.x;
     if (y == 0 && z > half) return;  // produced as the twin row of (0, N-z)
 
     // ---- phase 1: draw the primary modes of row (y, z) once ----
@@ -147,8 +148,14 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
         }
         fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
         const bool live = (side == 0) || has_twin;
-        const long long row = (side == 0) ? ((long long) a * N + z) * N * (long long) N + (long long) y * N
-                                           : ((long long) a * N + zh) * N * (long long) N + (long long) yh * N;
+        long long row;
+        if (sg.G == 1) {
+            row = (side == 0) ? ((long long) a * N + z) * N * (long long) N + (long long) y * N
+                              : ((long long) a * N + zh) * N * (long long) N + (long long) yh * N;
+        } else {
+            const int ly = (y == half) ? sg.h : y - sg.rank * sg.h;  // slot of the primary row
+            row = (side == 0) ? slab_b1_row(sg, a, z, ly) : slab_b1_row(sg, a, zh, (y == 0) ? 0 : sg.h + ly);
+        }
         if (live) {
 #pragma unroll
             for (int e = 0; e < 16; e++) st_stream(&cube[row + b + M * e], v[e]);
@@ -254,8 +261,9 @@ __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q
 // complete record fields.  A is a compile-time constant, the format test is CTA-uniform and
 // sits outside the element loops.
 template <int N, int T, int A>
-__device__ __forceinline__ void emit_array(const cplx *__restrict__ src, cplx *S, float *keep, const cplx *__restrict__ tw,
-                                           const EmitParams &ep, const RecLayout &L, unsigned char *rec0, long long z, int x,
+__device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const SlabGeom &sg, int zl, cplx *S, float *keep,
+                                           const cplx *__restrict__ tw, const EmitParams &ep, const RecLayout &L,
+                                           unsigned char *rec0, long long z, int x,
                                            int tid, int p, int b, bool first, double (*s_red)[8]) {
     constexpr int M  = N / 16;
     constexpr int NT = T * M;
@@ -264,7 +272,11 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, cplx *S
     const double vn = ep.vnorm;
     cplx v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = ld_stream(&src[(long long) (b + M * e) * N]);
+    for (int e = 0; e < 16; e++) {
+        // single GPU: rows of the [a][z][y][x] cube; slab rank: rows of the exchanged buffer B2
+        const long long off = (sg.G == 1) ? (long long) (b + M * e) * N : slab_b2_row(sg, A, zl, b + M * e);
+        v[e] = ld_stream(&src[off]);
+    }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
     fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
     if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]
@@ -362,7 +374,8 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, cplx *S
 
 template <int N, int T>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
-   fft_emit_strided_kernel(const cplx *__restrict__ cube, long long z_first, EmitParams ep, const cplx *__restrict__ tw) {
+   fft_emit_strided_kernel(const cplx *__restrict__ cube, SlabGeom sg, long long z_first, EmitParams ep,
+                           const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_red[32][8];
     constexpr int M  = N / 16;
@@ -370,17 +383,19 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     cplx *S      = reinterpret_cast<cplx *>(smem_raw);
     float *keep  = reinterpret_cast<float *>(smem_raw + (size_t) T * FftPlan<N>::PSTRIDE * sizeof(cplx));  // [2][16][NT]
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
-    const long long z = z_first + blockIdx.y;
-    const int x       = blockIdx.x * T + p;
-    const long long N3 = (long long) N * N * N;
-    const cplx *src    = cube + z * N * (long long) N + x;  // + a*N3 + y*N
+    // z_first counts this rank's planes; the particle id carries the global plane index
+    const long long zl = z_first + blockIdx.y;
+    const long long z  = (sg.G == 1) ? zl : (long long) sg.rank * (N / sg.G) + zl;
+    const int x        = blockIdx.x * T + p;
+    const long long N3 = (sg.G == 1) ? (long long) N * N * N : 0;
+    const cplx *src    = (sg.G == 1) ? cube + zl * N * (long long) N + x : cube + x;  // + a*N3 + y*N  |  + B2 row offset
     const RecLayout L  = rec_layout(ep.icformat);
-    unsigned char *rec0 = ep.out + ((size_t) ((z - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
+    unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
     // A0 and A2 first (their values wait in shared memory), then A1 and A3 complete the record halves
-    emit_array<N, T, 0>(src, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
-    if (ep.qPLT) emit_array<N, T, 2>(src + 2 * N3, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-    emit_array<N, T, 1>(src + N3, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-    if (ep.qPLT) emit_array<N, T, 3>(src + 3 * N3, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    emit_array<N, T, 0>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
+    if (ep.qPLT) emit_array<N, T, 2>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    emit_array<N, T, 1>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    if (ep.qPLT) emit_array<N, T, 3>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
     __syncthreads();
     if (tid < 7) {
         constexpr int NW = (NT >= 32) ? NT / 32 : NT;
@@ -493,13 +508,13 @@ static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStr
 }
 
 template <int N, int NP>
-static int launch_genx_t(const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st) {
+static int launch_genx_t(const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st) {
     if ((2 * g.na) % NP) return (int) cudaErrorInvalidValue;
     size_t smem = fft_tile_smem(N, NP) + (size_t) 6 * N * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gen_xfft_kernel<N, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    dim3 grid(N, N / 2 + 1, 1);
-    gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, cube, tw);
+    dim3 grid(N, sg.G == 1 ? N / 2 + 1 : sg.h + (sg.rank == 0 ? 1 : 0), 1);
+    gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, sg, cube, tw);
     return (int) cudaGetLastError();
 }
 
@@ -517,19 +532,19 @@ int gen_xfft_T(int N, int na) {
     }
 }
 
-int launch_gen_xfft(int N, int T, const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st) {
-    ZPLT_CASE(launch_genx_t, 16, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 32, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 64, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 128, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 256, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 512, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 512, 8, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 1024, 8, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 1024, 4, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 1024, 2, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 2048, 2, g, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 2048, 4, g, cube, tw, st)
+int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st) {
+    ZPLT_CASE(launch_genx_t, 16, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 32, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 64, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 128, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 256, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 512, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 512, 8, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 1024, 8, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 1024, 4, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 1024, 2, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 2048, 2, g, sg, cube, tw, st)
+    ZPLT_CASE(launch_genx_t, 2048, 4, g, sg, cube, tw, st)
     return (int) cudaErrorInvalidValue;
 }
 
@@ -551,32 +566,32 @@ int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &g, const cplx *tw
 }
 
 template <int N, int T>
-static int launch_emit_strided_t(const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
-                                 cudaStream_t st, int *launches) {
+static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long z_first, long long nz, const EmitParams &ep,
+                                 const cplx *tw, cudaStream_t st, int *launches) {
     size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
     dim3 grid(N / T, (unsigned) nz, 1);
-    fft_emit_strided_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(cube, z_first, ep, tw);
+    fft_emit_strided_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);
     if (launches) *launches += 1;
     return (int) cudaGetLastError();
 }
 
 // y-axis FFT + record emission for planes [z_first, z_first+nz); the cube holds the x- and z-transformed arrays
-int launch_fft_emit_strided(int N, int T, const cplx *cube, long long z_first, long long nz, const EmitParams &ep,
-                            const cplx *tw, cudaStream_t st, int *launches) {
-    ZPLT_CASE(launch_emit_strided_t, 16, 16, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 32, 32, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 64, 32, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 128, 16, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 256, 16, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 256, 8, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 512, 8, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 512, 4, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 1024, 4, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 2048, 2, cube, z_first, nz, ep, tw, st, launches)
+int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
+                            const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches) {
+    ZPLT_CASE(launch_emit_strided_t, 16, 16, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 32, 32, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 64, 32, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 128, 16, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 256, 16, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 256, 8, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 512, 8, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 512, 4, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 1024, 4, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, sg, z_first, nz, ep, tw, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 2048, 2, cube, sg, z_first, nz, ep, tw, st, launches)
     return (int) cudaErrorInvalidValue;
 }
 

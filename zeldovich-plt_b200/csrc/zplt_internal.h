@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "zplt_device.cuh"
+#include "zplt_slab.h"
 
 namespace zplt {
 
@@ -35,12 +36,12 @@ int fft_tile_T(int N);            // pencils per CTA used for length N (strided 
 int gen_xfft_T(int N, int na);    // pencils per CTA of the generation + x-FFT kernel
 size_t fft_tile_smem(int N, int T);
 // Fused mode generation + x-axis FFT, writes the whole [na][z][y][x] cube.
-int launch_gen_xfft(int N, int T, const GenParams &g, cplx *cube, const cplx *tw, cudaStream_t st);
+int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st);
 // In-place backward FFT of every pencil described by geom (tiles of T pencils).  Returns cudaError_t.
 int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
 // y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
-int launch_fft_emit_strided(int N, int T, const cplx *cube, long long z_first, long long nz, const EmitParams &ep,
-                            const cplx *tw, cudaStream_t st, int *launches);
+int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
+                            const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches);
 // Record emission for planes [z_first, z_first+nz) of a fully transformed [na][N][N][N] cube.
 int launch_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st, int *launches);
 

@@ -1,0 +1,46 @@
+"""Slab-decomposed runs: one process per GPU, ``torch.distributed`` for the plumbing.
+
+Stage 1 (generation, x and z transforms) is sharded over y-row pairs, stage 2 (y transform and
+emission) over z planes; between them every rank sends block r of its stage-1 buffer to rank r —
+one all-to-all, the y<->z transpose the reference does through ``BlockArray``
+(reference src/block_array.cpp:387-414, 466-504).  The layout math lives in ``csrc/zplt_slab.h``
+(device + host); this module only moves the blocks.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+def exchange_tensors(send: torch.Tensor, recv: torch.Tensor, group=None) -> None:
+    """all-to-all of equal contiguous blocks: block r of ``send`` goes to rank r, ``recv`` is filled in
+    rank order.  Works on any backend (nccl for device tensors, gloo on CPU)."""
+    world = dist.get_world_size(group)
+    assert send.numel() == recv.numel() and send.numel() % world == 0
+    dist.all_to_all_single(recv, send, group=group)
+
+
+class SlabWorkspace:
+    """Torch-owned workspace of a slab context: [send | recv] halves, viewed as float64."""
+
+    def __init__(self, ctx, device):
+        self.ctx = ctx
+        nbytes = ctx.workspace_bytes()
+        self.buf = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
+        ctx.set_workspace(self.buf.data_ptr(), nbytes)
+        send_ptr, recv_ptr, self.bytes_per_peer = ctx.exchange_info()
+        half = self.buf.numel() // 2
+        assert send_ptr == self.buf.data_ptr() and recv_ptr == self.buf.data_ptr() + half * 8
+        self.send = self.buf[:half]
+        self.recv = self.buf[half:]
+
+    def exchange(self, group=None):
+        """Run the all-to-all on the current torch stream and mark the context as exchanged."""
+        exchange_tensors(self.send, self.recv, group)
+        self.ctx.exchange_done()
+
+
+def plane_range(ppd: int, rank: int, world: int):
+    """Global z planes [z0, z1) rank owns in stage 2."""
+    n = ppd // world
+    return rank * n, (rank + 1) * n
