@@ -247,21 +247,43 @@ def main_b200(args, rank, world, local_rank):
     P = pkg.Parameters(par)
     power = pkg.PowerSpectrum(P)
     cfg = P.config(device=local_rank)
+    cfg.rank, cfg.nranks = rank, world  # world > 1: slab decomposition, one all-to-all per step
     ctx = pkg.Context(cfg)
     rb = ctx.record_bytes
+    nloc = N // world  # z planes this rank emits
 
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
-    work = torch.empty(ctx.workspace_bytes(), dtype=torch.uint8, device=dev)
-    ctx.set_workspace(work.data_ptr(), work.numel())
-    out = torch.empty(N * N * N * rb, dtype=torch.uint8, device=dev)
+    if world > 1:
+        import importlib.util
+
+        from __graft_entry__ import PKG_DIR
+
+        spec = importlib.util.spec_from_file_location("zplt_distributed", os.path.join(PKG_DIR, "distributed.py"))
+        zd = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(zd)
+        ws = zd.SlabWorkspace(ctx, dev)
+    else:
+        work = torch.empty(ctx.workspace_bytes(), dtype=torch.uint8, device=dev)
+        ctx.set_workspace(work.data_ptr(), work.numel())
+    # records stay in HBM; if the full set does not fit beside the slabs, planes cycle through a smaller buffer
+    free_b = torch.cuda.mem_get_info(dev)[0]
+    plane_b = N * N * rb
+    out_planes = max(1, min(nloc, int((free_b - (6 << 30)) // plane_b)))
+    out = torch.empty(out_planes * plane_b, dtype=torch.uint8, device=dev)
     power.apply(ctx)
     if qplt:
         ctx.load_eigenmodes_file(P.PLT_filename)
+    a2a_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
     def step():
         ctx.generate()
-        ctx.emit_planes(0, N, out.data_ptr())
+        if world > 1:
+            a2a_ev[0].record(stream)
+            ws.exchange()
+            a2a_ev[1].record(stream)
+        for z0 in range(0, nloc, out_planes):
+            ctx.emit_planes(z0, min(out_planes, nloc - z0), out.data_ptr())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -269,14 +291,13 @@ def main_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = [0.0, 0.0, 0.0, 0.0]
-    launches = 0
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -288,19 +309,21 @@ def main_b200(args, rank, world, local_rank):
     total_ms = e0.elapsed_time(e1)
     tm = ctx.timings()
     stage = [tm["generate_ms"], tm["zfft_ms"], tm["xfft_emit_ms"]]
+    a2a_ms = a2a_ev[0].elapsed_time(a2a_ev[1]) if world > 1 else 0.0
     launches = sum(tm["launches"]) * args.steps
     clocks = sampler.stop()
-    ms = torch.tensor([total_ms / args.steps], dtype=torch.float64, device=dev)
+    red = torch.tensor([total_ms / args.steps, a2a_ms] + stage, dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item())
-    stats = ctx.stats()
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    ms_per_step = float(red[0].item())
+    a2a_ms = float(red[1].item())
+    stage = [float(v) for v in red[2:].tolist()]
 
     # ---- end to end through the C ABI with host buffers --------------------------------
     e2e = None
     if not args.no_e2e:
         plane = N * N * rb
-        chunk = max(1, min(N, (2 << 30) // plane))
+        chunk = max(1, min(nloc, (2 << 30) // plane))
         pinned = torch.empty(chunk * plane, dtype=torch.uint8, pin_memory=True)
         x, y, y2 = power.arrays()
         eig_tab = synth.read_eigmodes(P.PLT_filename)[1] if qplt else None
@@ -311,9 +334,12 @@ def main_b200(args, rank, world, local_rank):
             ctx.set_power_spline(x, y, y2, power.normalization, power.Pk_smooth2)  # H2D + table kernel
             if qplt:
                 ctx.set_eigenmodes(128, eig_tab)  # H2D
-            ctx.generate()
-            for z0 in range(0, N, chunk):
-                ctx.fetch_planes_ptr(z0, min(chunk, N - z0), pinned.data_ptr())  # D2H of every record
+            with torch.cuda.stream(stream):
+                ctx.generate()
+                if world > 1:
+                    ws.exchange()
+            for z0 in range(0, nloc, chunk):
+                ctx.fetch_planes_ptr(z0, min(chunk, nloc - z0), pinned.data_ptr())  # D2H of every record
 
         e2e_step()
         barrier()
@@ -324,7 +350,7 @@ def main_b200(args, rank, world, local_rank):
         dt = torch.tensor([(time.perf_counter() - t0) / nsteps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * N**3 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": N**3 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(N**3 * rb), "steps": nsteps, "seconds_per_step": float(dt.item()),
                "note": "host spline+eigenmode tables -> device, records -> pinned host in 2 GiB chunks, wall clock"}
 
@@ -332,7 +358,7 @@ def main_b200(args, rank, world, local_rank):
         peak, peak_src = peaks()
         # dominant kernel = the slower of the two strided FFT passes (K2: read + write 16*narray B per particle each way)
         names = ["generate+x-FFT", "z-FFT", "y-FFT+emit"]
-        alg_bytes = [16 * na * N**3, 32 * na * N**3, (16 * na + rb) * N**3]  # write; read+write; read+records
+        alg_bytes = [v // world for v in (16 * na * N**3, 32 * na * N**3, (16 * na + rb) * N**3)]  # per GPU: write; r+w; read+records
         dom = 1  # the in-place strided pass (z axis): reads and writes every array once
         achieved = alg_bytes[dom] / (stage[dom] * 1e-3) / 1e9
         traffic = None
@@ -343,12 +369,13 @@ def main_b200(args, rank, world, local_rank):
             except Exception:
                 traffic = None
         line = {
-            "metric": METRIC, "value": world * N**3 / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": N**3 / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"PPD={N} {'qPLT+rescale' if qplt else 'ZA'} {args.icformat}, synthetic BBKS P(k) + synthetic eigmodes128",
                        "ppd": N, "narray": na, "record_bytes": rb,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab decomposition not built yet)",
+                       "parallelism": "single GPU" if world == 1 else f"slab decomposition over {world} GPUs: y-row pairs -> NCCL all_to_all_single -> z planes",
                        "l2": f"inputs larger than L2 ({16 * na * N**3 / 1e9:.1f} GB spectral arrays streamed per pass)"},
             "stage_ms": dict(zip(names, stage)),
             "stage_gbs": {n: alg_bytes[i] / (stage[i] * 1e-3) / 1e9 for i, n in enumerate(names)},
@@ -356,6 +383,10 @@ def main_b200(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes[dom]},
             "clocks": clocks, "gpu_launches": launches,
+            "all_to_all": None if world == 1 else {
+                "ms": a2a_ms, "bytes_sent_per_gpu": int(16 * na * N**3 // world * (world - 1) // world),
+                "nvlink_gbs_per_gpu": 16 * na * N**3 / world * (world - 1) / world / (a2a_ms * 1e-3) / 1e9,
+                "reference_peer_copy_gbs": 770.0},
             "stats": {"rms_density": (stats["density_variance"] / args.steps / max(args.warmup + 1, 1) / N**3) ** 0.5
                       if False else None},
         }

@@ -167,6 +167,8 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
         CK(cudaEventCreateWithFlags(&c->stage_full[i], cudaEventDisableTiming));
     }
     c->sg.N = (int) N, c->sg.G = cfg->nranks, c->sg.rank = cfg->rank, c->sg.h = (int) (N / (2 * cfg->nranks)), c->sg.na = c->na;
+    c->sg.log2h = 0;
+    while ((1 << c->sg.log2h) < c->sg.h) c->sg.log2h++;
     c->slab_elems = (size_t) c->na * N * N * N / cfg->nranks;
     // one buffer on a single GPU; stage-1 + stage-2 buffers when the grid is slab-decomposed
     c->cube_bytes = c->slab_elems * sizeof(cplx) * (cfg->nranks > 1 ? 2 : 1);
@@ -514,6 +516,8 @@ extern "C" int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray,
                                     int64_t y) {
     SlabGeom g;
     g.N = (int) ppd, g.G = nranks, g.rank = rank, g.h = (int) (ppd / (2 * nranks)), g.na = narray;
+    g.log2h = 0;
+    while ((1 << g.log2h) < g.h) g.log2h++;
     if (stage == 1) {  // where rank `rank` (the owner of row y) keeps row (a, z, y) before the exchange
         int r, s;
         slab_owner(g.N, g.G, (int) y, r, s);

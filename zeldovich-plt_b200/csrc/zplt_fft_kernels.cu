@@ -260,7 +260,7 @@ __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q
 // One packed array A of the tile: load, transform along y, then either park its values or
 // complete record fields.  A is a compile-time constant, the format test is CTA-uniform and
 // sits outside the element loops.
-template <int N, int T, int A>
+template <int N, int T, int A, bool SLAB>
 __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const SlabGeom &sg, int zl, cplx *S, float *keep,
                                            const cplx *__restrict__ tw, const EmitParams &ep, const RecLayout &L,
                                            unsigned char *rec0, long long z, int x,
@@ -274,7 +274,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         // single GPU: rows of the [a][z][y][x] cube; slab rank: rows of the exchanged buffer B2
-        const long long off = (sg.G == 1) ? (long long) (b + M * e) * N : slab_b2_row(sg, A, zl, b + M * e);
+        const long long off = SLAB ? slab_b2_row(sg, A, zl, b + M * e) : (long long) (b + M * e) * N;
         v[e] = ld_stream(&src[off]);
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
@@ -372,7 +372,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
     }
 }
 
-template <int N, int T>
+template <int N, int T, bool SLAB>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
    fft_emit_strided_kernel(const cplx *__restrict__ cube, SlabGeom sg, long long z_first, EmitParams ep,
                            const cplx *__restrict__ tw) {
@@ -385,17 +385,17 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     // z_first counts this rank's planes; the particle id carries the global plane index
     const long long zl = z_first + blockIdx.y;
-    const long long z  = (sg.G == 1) ? zl : (long long) sg.rank * (N / sg.G) + zl;
+    const long long z  = SLAB ? (long long) sg.rank * (N / sg.G) + zl : zl;
     const int x        = blockIdx.x * T + p;
-    const long long N3 = (sg.G == 1) ? (long long) N * N * N : 0;
-    const cplx *src    = (sg.G == 1) ? cube + zl * N * (long long) N + x : cube + x;  // + a*N3 + y*N  |  + B2 row offset
+    const long long N3 = SLAB ? 0 : (long long) N * N * N;
+    const cplx *src    = SLAB ? cube + x : cube + zl * N * (long long) N + x;  // + B2 row offset  |  + a*N3 + y*N
     const RecLayout L  = rec_layout(ep.icformat);
     unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
     // A0 and A2 first (their values wait in shared memory), then A1 and A3 complete the record halves
-    emit_array<N, T, 0>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
-    if (ep.qPLT) emit_array<N, T, 2>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-    emit_array<N, T, 1>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-    if (ep.qPLT) emit_array<N, T, 3>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    emit_array<N, T, 0, SLAB>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
+    if (ep.qPLT) emit_array<N, T, 2, SLAB>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    emit_array<N, T, 1, SLAB>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    if (ep.qPLT) emit_array<N, T, 3, SLAB>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
     __syncthreads();
     if (tid < 7) {
         constexpr int NW = (NT >= 32) ? NT / 32 : NT;
@@ -569,10 +569,17 @@ template <int N, int T>
 static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long z_first, long long nz, const EmitParams &ep,
                                  const cplx *tw, cudaStream_t st, int *launches) {
     size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return (int) e;
     dim3 grid(N / T, (unsigned) nz, 1);
-    fft_emit_strided_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);
+    cudaError_t e;
+    if (sg.G > 1) {
+        e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        fft_emit_strided_kernel<N, T, true><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);
+    } else {
+        e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        fft_emit_strided_kernel<N, T, false><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);
+    }
     if (launches) *launches += 1;
     return (int) cudaGetLastError();
 }

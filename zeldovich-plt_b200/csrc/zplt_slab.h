@@ -31,8 +31,9 @@ struct SlabGeom {
     int N;     // ppd
     int G;     // ranks
     int rank;  // this rank
-    int h;     // primary rows per rank = N / (2G)
+    int h;     // primary rows per rank = N / (2G)  (a power of two, like N and G)
     int na;    // packed arrays
+    int log2h;
 };
 
 // which rank owns row y, and in which of its 2h slots
@@ -64,8 +65,17 @@ ZPLT_HD long long slab_b1_row(const SlabGeom &s, int a, int z, int slot) {
     return (((long long) z * s.na + a) * (2 * s.h) + slot) * (long long) s.N;
 }
 ZPLT_HD long long slab_b2_row(const SlabGeom &s, int a, int zl, int y) {
+    // slab_owner() with the divisions by h done as shifts
+    const int half = s.N / 2, hm = s.h - 1;
     int src, slot;
-    slab_owner(s.N, s.G, y, src, slot);
+    if (y < half) {
+        src = y >> s.log2h, slot = y & hm;
+    } else if (y == half) {
+        src = 0, slot = s.h;
+    } else {
+        const int yp = s.N - y;
+        src = yp >> s.log2h, slot = s.h + (yp & hm);
+    }
     return ((((long long) src * (s.N / s.G) + zl) * s.na + a) * (2 * s.h) + slot) * (long long) s.N;
 }
 // complex elements every rank sends to every other rank
