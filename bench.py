@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--ref-ppd", type=int, default=0, help="PPD of the CPU-reference sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: z-pass kernel stores into peer memory (p2p) or NCCL all_to_all_single")
     return ap.parse_args()
 
 
@@ -262,7 +264,7 @@ def main_b200(args, rank, world, local_rank):
         spec = importlib.util.spec_from_file_location("zplt_distributed", os.path.join(PKG_DIR, "distributed.py"))
         zd = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(zd)
-        ws = zd.SlabWorkspace(ctx, dev)
+        ws = zd.PeerExchange(ctx) if args.exchange == "p2p" else zd.SlabWorkspace(ctx, dev)
     else:
         work = torch.empty(ctx.workspace_bytes(), dtype=torch.uint8, device=dev)
         ctx.set_workspace(work.data_ptr(), work.numel())
@@ -375,7 +377,10 @@ def main_b200(args, rank, world, local_rank):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"PPD={N} {'qPLT+rescale' if qplt else 'ZA'} {args.icformat}, synthetic BBKS P(k) + synthetic eigmodes128",
                        "ppd": N, "narray": na, "record_bytes": rb,
-                       "parallelism": "single GPU" if world == 1 else f"slab decomposition over {world} GPUs: y-row pairs -> NCCL all_to_all_single -> z planes",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"slab decomposition over {world} GPUs: y-row pairs -> "
+                           + ("z-FFT kernel storing into peer memory over NVLink (CUDA IPC)" if args.exchange == "p2p" else "NCCL all_to_all_single")
+                           + " -> z planes"),
                        "l2": f"inputs larger than L2 ({16 * na * N**3 / 1e9:.1f} GB spectral arrays streamed per pass)"},
             "stage_ms": dict(zip(names, stage)),
             "stage_gbs": {n: alg_bytes[i] / (stage[i] * 1e-3) / 1e9 for i, n in enumerate(names)},
@@ -384,8 +389,11 @@ def main_b200(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": alg_bytes[dom]},
             "clocks": clocks, "gpu_launches": launches,
             "all_to_all": None if world == 1 else {
+                "how": args.exchange,
+                # p2p: the exchange IS the z-FFT kernel (stage_ms["z-FFT"]); "ms" then only holds the sync + barrier
                 "ms": a2a_ms, "bytes_sent_per_gpu": int(16 * na * N**3 // world * (world - 1) // world),
-                "nvlink_gbs_per_gpu": 16 * na * N**3 / world * (world - 1) / world / (a2a_ms * 1e-3) / 1e9,
+                "nvlink_gbs_per_gpu": 16 * na * N**3 / world * (world - 1) / world
+                / ((stage[1] if args.exchange == "p2p" else a2a_ms) * 1e-3) / 1e9,
                 "reference_peer_copy_gbs": 770.0},
             "stats": {"rms_density": (stats["density_variance"] / args.steps / max(args.warmup + 1, 1) / N**3) ** 0.5
                       if False else None},

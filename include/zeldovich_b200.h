@@ -122,6 +122,15 @@ int zplt_fetch_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *host_out);
  * LOCAL index (global z = rank*ppd/nranks + local); particle ids carry the global index. */
 int zplt_exchange_info(zplt_ctx *ctx, void **send, void **recv, size_t *bytes_per_peer);
 int zplt_exchange_done(zplt_ctx *ctx);
+/* Fused exchange over NVLink peer memory (one process per GPU on one node).  Every rank exports a
+ * 64-byte CUDA IPC handle of its library-owned workspace (zplt_ipc_export; do not call
+ * zplt_set_workspace), the caller gathers the handles in rank order (e.g. torch.distributed
+ * all_gather) and hands them to zplt_ipc_import.  From then on zplt_generate's z-axis FFT kernel
+ * stores its results straight into the owner ranks' receive buffers — no separate all-to-all
+ * pass.  The caller still has to synchronise the stream and run a barrier across ranks before
+ * zplt_exchange_done(): a rank may only read its planes once every peer has finished writing. */
+int zplt_ipc_export(zplt_ctx *ctx, void *handle64);
+int zplt_ipc_import(zplt_ctx *ctx, int32_t nranks, const void *handles);
 /* Layout of the decomposition (host mirror of the device index math, for tests and bindings):
  * which rank owns row y in stage 1 and in which of its slots. */
 int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32_t *slot);

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ppd", type=int, default=256)
     ap.add_argument("--za", action="store_true")
+    ap.add_argument("--p2p", action="store_true", help="fused exchange: z-pass kernel stores into peer memory over NVLink")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -53,11 +54,16 @@ def main():
     ctx = make(rank, world)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
-    ws = zd.SlabWorkspace(ctx, dev)
-    with torch.cuda.stream(stream):
+    if args.p2p:
+        ws = zd.PeerExchange(ctx)
         ctx.generate()
         ws.exchange()
-    stream.synchronize()
+    else:
+        ws = zd.SlabWorkspace(ctx, dev)
+        with torch.cuda.stream(stream):
+            ctx.generate()
+            ws.exchange()
+        stream.synchronize()
     mine = ctx.fetch_planes(0, N // world)
     st = ctx.stats()
     ctx.close()
@@ -73,7 +79,7 @@ def main():
         want = ref_ctx.fetch_planes(0, N).view(np.uint8)
         rst = ref_ctx.stats()
         same = np.array_equal(got, want)
-        print(f"slab run PPD={N} world={world}: records identical to single-GPU run: {same}; "
+        print(f"slab run PPD={N} world={world} p2p={args.p2p}: records identical to single-GPU run: {same}; "
               f"density variance {var:.12g} vs {rst['density_variance']:.12g}")
         assert same
     dist.barrier()

@@ -89,7 +89,7 @@ EXPORTS = [
     "zplt_create", "zplt_destroy", "zplt_last_error", "zplt_record_bytes", "zplt_narray", "zplt_set_power_spline",
     "zplt_set_power_law", "zplt_set_eigenmodes", "zplt_workspace_bytes", "zplt_set_workspace", "zplt_set_stream",
     "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
-    "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
+    "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
     "zplt_power_sigmaR", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
@@ -130,6 +130,8 @@ def lib():
     L.zplt_get_timings.argtypes = [vp, dp]
     L.zplt_exchange_info.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.zplt_exchange_done.argtypes = [vp]
+    L.zplt_ipc_export.argtypes = [vp, C.c_char_p]
+    L.zplt_ipc_import.argtypes = [vp, i32, C.c_char_p]
     L.zplt_slab_owner.argtypes = [i64, i32, i64, C.POINTER(i32), C.POINTER(i32)]
     L.zplt_slab_offset.argtypes = [i64, i32, i32, i32, i32, i32, i64, i64]
     L.zplt_slab_offset.restype = i64
@@ -320,6 +322,16 @@ class Context:
         send, recv, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
         _ck(lib().zplt_exchange_info(self._h, C.byref(send), C.byref(recv), C.byref(nb)))
         return send.value, recv.value, nb.value
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(64)
+        _ck(lib().zplt_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_import(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        _ck(lib().zplt_ipc_import(self._h, len(handles), blob))
 
     def exchange_done(self):
         _ck(lib().zplt_exchange_done(self._h))

@@ -76,6 +76,9 @@ struct zplt_ctx {
     SlabGeom sg;
     size_t slab_elems;  // complex elements of one slab buffer
     bool exchanged;
+    bool p2p;               // peers' stage-2 buffers are mapped: the z pass stores straight into them
+    cplx *peer_recv[16];
+    void *peer_base[16];    // what cudaIpcOpenMemHandle returned (to close)
     double vnorm;
     cudaStream_t stream, copy_stream;
     bool own_stream;
@@ -248,6 +251,8 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < 16; r++)
+        if (c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->own_cube && c->cube) cudaFree(c->cube);
     cudaFree(c->ptab);
     cudaFree(c->spx);
@@ -409,7 +414,10 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
             g.tstride = T, g.grid_x = c->N / T, g.pa = T, g.plo_stride = 1, g.phi_stride = 0;
             g.nstride = (long long) c->na * 2 * c->sg.h * c->N;
         }
-        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->stream));
+        if (slab && c->p2p)
+            CK(launch_fft_tiles_p2p(c->N, fft_tile_T(c->N), c->cube, c->sg, c->peer_recv, c->tw, c->stream));
+        else
+            CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->stream));
         c->launches[1] = 1;
     }
     CK(cudaEventRecord(c->ev_gen[2], c->stream));
@@ -494,6 +502,41 @@ extern "C" int zplt_exchange_info(zplt_ctx *c, void **send, void **recv, size_t 
     if (send) *send = c->cube;
     if (recv) *recv = c->cube + c->slab_elems;
     if (bytes_per_peer) *bytes_per_peer = (size_t) slab_block_elems(c->sg) * sizeof(cplx);
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_ipc_export(zplt_ctx *c, void *handle64) {
+    if (!c || !handle64) return fail(ZPLT_EINVAL, "null argument");
+    if (c->sg.G == 1) return fail(ZPLT_EINVAL, "a single-GPU context has no exchange");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaSetDevice(c->device));
+    if (c->cube && !c->own_cube) return fail(ZPLT_ESTATE, "peer exchange needs the library-owned workspace (do not call zplt_set_workspace)");
+    int rc = ensure_cube(c);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->cube));
+    memcpy(handle64, &h, 64);
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_ipc_import(zplt_ctx *c, int32_t nranks, const void *handles) {
+    if (!c || !handles) return fail(ZPLT_EINVAL, "null argument");
+    if (nranks != c->sg.G || nranks > 16) return fail(ZPLT_EINVAL, "expected %d handles (at most 16 ranks)", c->sg.G);
+    CK(cudaSetDevice(c->device));
+    if (!c->cube || !c->own_cube) return fail(ZPLT_ESTATE, "call zplt_ipc_export first");
+    for (int r = 0; r < nranks; r++) {
+        if (r == c->sg.rank) {
+            c->peer_recv[r] = c->cube + c->slab_elems;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *) handles + 64 * r, 64);
+        void *base = nullptr;
+        CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_base[r] = base;
+        c->peer_recv[r] = (cplx *) base + c->slab_elems;
+    }
+    c->p2p = true;
     return ZPLT_OK;
 }
 

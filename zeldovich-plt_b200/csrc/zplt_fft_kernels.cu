@@ -164,6 +164,38 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     }
 }
 
+// z-axis pass of a slab rank with the exchange fused in: the transformed pencil is not written
+// back to the local stage-1 buffer but straight into the stage-2 buffers of the ranks that own
+// its planes — peer stores over NVLink (peer[r] is rank r's stage-2 base, opened through CUDA
+// IPC; peer[rank] is local).  This is BlockArray::StoreBlock + LoadBlock
+// (reference src/block_array.cpp:387-414, 466-504) done by the FFT epilogue, 128-byte runs.
+struct PeerTable {
+    cplx *recv[16];
+};
+template <int N, int T>
+__global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
+   fft_tile_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, PeerTable peers, const cplx *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *S         = reinterpret_cast<cplx *>(smem_raw);
+    constexpr int M = N / 16;
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    const int rows = sg.na * 2 * sg.h;          // x-rows per z plane of the stage-1 buffer
+    const int row  = blockIdx.y;                // a * 2h + slot
+    const int x    = blockIdx.x * T + p;
+    const long long nstride = (long long) rows * N;
+    const long long base    = (long long) row * N + x;
+    cplx v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
+    fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+    const int np = N / sg.G;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int z = b + M * e, r = z / np, zl = z % np;
+        st_stream(&peers.recv[r][(((long long) sg.rank * np + zl) * rows + row) * N + x], v[e]);
+    }
+}
+
 // byte offsets inside one record, per ICFormat (reference include/output.h:19-42)
 struct RecLayout {
     int off_ijk;   // -1: no ids
@@ -545,6 +577,31 @@ int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *
     ZPLT_CASE(launch_genx_t, 1024, 2, g, sg, cube, tw, st)
     ZPLT_CASE(launch_genx_t, 2048, 2, g, sg, cube, tw, st)
     ZPLT_CASE(launch_genx_t, 2048, 4, g, sg, cube, tw, st)
+    return (int) cudaErrorInvalidValue;
+}
+
+template <int N, int T>
+static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, cudaStream_t st) {
+    size_t smem = fft_tile_smem(N, T);
+    cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    PeerTable pt;
+    for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
+    dim3 grid(N / T, sg.na * 2 * sg.h, 1);
+    fft_tile_p2p_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(b1, sg, pt, tw);
+    return (int) cudaGetLastError();
+}
+
+int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
+                         cudaStream_t st) {
+    if (sg.G > 16) return (int) cudaErrorInvalidValue;
+    ZPLT_CASE(launch_tiles_p2p_t, 32, 32, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 64, 32, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 128, 16, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 256, 16, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 512, 8, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 1024, 8, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 2048, 4, b1, sg, peer_recv, tw, st)
     return (int) cudaErrorInvalidValue;
 }
 

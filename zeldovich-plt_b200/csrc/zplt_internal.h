@@ -39,6 +39,10 @@ size_t fft_tile_smem(int N, int T);
 int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st);
 // In-place backward FFT of every pencil described by geom (tiles of T pencils).  Returns cudaError_t.
 int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+// z-axis FFT of a slab rank's stage-1 buffer with the exchange fused in: results are stored
+// directly into every owner rank's stage-2 buffer (peer_recv[r], NVLink peer memory).
+int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
+                         cudaStream_t st);
 // y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
                             const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches);

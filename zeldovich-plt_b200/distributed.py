@@ -44,3 +44,23 @@ def plane_range(ppd: int, rank: int, world: int):
     """Global z planes [z0, z1) rank owns in stage 2."""
     n = ppd // world
     return rank * n, (rank + 1) * n
+
+
+class PeerExchange:
+    """Fused exchange: the z-pass kernel stores into the peers' stage-2 buffers over NVLink
+    (CUDA IPC mapped peer memory).  ``torch.distributed`` only carries the 64-byte handles and
+    the barrier that separates the writers from the readers."""
+
+    def __init__(self, ctx, group=None):
+        self.ctx, self.group = ctx, group
+        world = dist.get_world_size(group)
+        mine = ctx.ipc_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        ctx.ipc_import(handles)
+
+    def exchange(self):
+        """Call after ctx.generate(): wait for this rank's peer stores, then for everybody else's."""
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)
+        self.ctx.exchange_done()
