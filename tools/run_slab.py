@@ -20,6 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ppd", type=int, default=256)
     ap.add_argument("--za", action="store_true")
+    ap.add_argument("--oversample-check", action="store_true",
+                    help="run PPD with ZD_k_cutoff=2 and compare even lattice sites with a single-GPU PPD/2 run (ZA only)")
     ap.add_argument("--p2p", action="store_true", help="fused exchange: z-pass kernel stores into peer memory over NVLink")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -35,6 +37,9 @@ def main():
     tmp = tempfile.mkdtemp(prefix=f"zslab{rank}_")
     synth.write_power_table(os.path.join(tmp, "pk.pow"))
     over = dict(NP=N**3, ICFormat='"RVZel"', ZD_Pk_filename='"%s"' % os.path.join(tmp, "pk.pow"))
+    if args.oversample_check:
+        assert args.za, "the oversampling identity holds for ZA only (PLT eigenmodes depend on the lattice)"
+        over["ZD_k_cutoff"] = "2.0"
     if not args.za:
         synth.write_eigmodes(os.path.join(tmp, "eig"), 128)
         over.update(ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="5.0", ZD_PLT_filename='"%s"' % os.path.join(tmp, "eig"))
@@ -68,6 +73,39 @@ def main():
     st = ctx.stats()
     ctx.close()
     del ws
+    if args.oversample_check:
+        # SURVEY §4 identity: PPD=N with k_cutoff=2 sampled at even sites == PPD=N/2 (same modes, same phases)
+        torch.cuda.empty_cache()
+        par2 = synth.write_param(os.path.join(tmp, "half.par"), **dict(over, NP=(N // 2) ** 3, ZD_k_cutoff="1.0"))
+        P2 = pkg.Parameters(par2)
+        pw2 = pkg.PowerSpectrum(P2)
+        c2 = pkg.Context(P2.config(device=local))
+        pw2.apply(c2)
+        c2.generate()
+        np_loc = N // world
+        worst, nchk = 0.0, 0
+        rec = mine.reshape(np_loc, N, N)
+        for zl in range(0, np_loc, max(2, np_loc // 8 // 2 * 2)):
+            zg = rank * np_loc + zl
+            if zg % 2:
+                continue
+            ref = c2.fetch_planes(zg // 2, 1).reshape(N // 2, N // 2)
+            sub = rec[zl, ::2, ::2]
+            assert np.array_equal(sub["ijk"] // 2, ref["ijk"]) and np.all(sub["ijk"] % 2 == 0)
+            for f in ("displ", "vel"):
+                d = np.abs(sub[f].astype(np.float64) - ref[f].astype(np.float64)).max() / np.abs(ref[f]).max()
+                worst = max(worst, float(d))
+            nchk += 1
+        c2.close()
+        t = torch.tensor([worst], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"oversample check PPD={N} (k_cutoff=2) vs PPD={N // 2}: {nchk} planes per rank, worst field-relative "
+                  f"difference {t.item():.3e} (float32 records)")
+        assert t.item() < 2e-7
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # gather on rank 0 and compare with a single-GPU run
     parts = [None] * world
     dist.gather_object((mine.view(np.uint8), st), parts if rank == 0 else None, dst=0)
