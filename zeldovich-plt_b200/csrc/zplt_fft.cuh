@@ -78,6 +78,28 @@ __device__ __forceinline__ void dft16(cplx (&v)[16]) {
     }
 }
 
+// w^1 .. w^(R-1) from w by a shallow multiplication tree (depth <= 4 products, error ~ a few ulp)
+// instead of R-1 table loads: the FP64 pipe has head-room, the load/store unit does not.
+template <int R>
+__device__ __forceinline__ void twiddle_powers(cplx w, cplx (&pw)[16]) {
+    pw[1] = w;
+    if (R > 2) {
+        pw[2] = cmul(w, w);
+        pw[3] = cmul(pw[2], w);
+    }
+    if (R > 4) {
+        pw[4] = cmul(pw[2], pw[2]);
+        pw[5] = cmul(pw[4], w);
+        pw[6] = cmul(pw[4], pw[2]);
+        pw[7] = cmul(pw[4], pw[3]);
+    }
+    if (R > 8) {
+        pw[8] = cmul(pw[4], pw[4]);
+#pragma unroll
+        for (int k = 9; k < 16; k++) pw[k] = cmul(pw[8], pw[k - 8]);
+    }
+}
+
 // R-point DFTs on consecutive groups of a 16-register array: group j uses v[j*R .. j*R+R-1]
 template <int R>
 __device__ __forceinline__ void dft_groups(cplx (&v)[16]);
@@ -134,10 +156,12 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
         for (int j = 0; j < NB; j++) {
             const int q  = b + j * M;
             const int kk = q / L, l = q % L;
+            cplx pw[16];
+            twiddle_powers<R>(__ldg(&tw[K * l]), pw);
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 cplx x = v[j * R + k];
-                if (k > 0) x = cmul(x, __ldg(&tw[K * l * k]));
+                if (k > 0) x = cmul(x, pw[k]);
                 S[(kk + K * k) * L + l] = x;
             }
         }
@@ -154,11 +178,15 @@ __device__ __forceinline__ void fft_pencil(cplx (&v)[16], cplx *S, int b, const 
     // pass 1: radix 16 over stride M, K = 1, L = M
     dft16(v);
     if constexpr (P::PASSES > 1) {
+    {
+        cplx pw[16];
+        twiddle_powers<16>(__ldg(&tw[b]), pw);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        cplx x = v[k];
-        if (k > 0) x = cmul(x, __ldg(&tw[b * k]));
-        S[k * P::M + b] = x;
+        for (int k = 0; k < 16; k++) {
+            cplx x = v[k];
+            if (k > 0) x = cmul(x, pw[k]);
+            S[k * P::M + b] = x;
+        }
     }
     __syncthreads();
     if constexpr (P::PASSES == 2) {

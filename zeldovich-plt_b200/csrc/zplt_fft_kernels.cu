@@ -43,21 +43,43 @@ __device__ __forceinline__ void st_stream(cplx *p, cplx v) {
 // resident CTAs per SM the register budget is tuned for: 512 threads of 128 registers fill an SM
 constexpr int min_ctas(int threads) { return threads >= 512 ? 1 : (512 / threads > 8 ? 8 : 512 / threads); }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One CTA per tile by default (x tile fastest, so that CTAs running at the same time cover
+// neighbouring 128-byte runs).  Two measured-and-rejected variants stay behind environment
+// switches for experiments: ZPLT_PERSIST=1 (persistent CTAs walking tiles: 36.0 vs 34.6 ms per
+// pass at PPD=1024 — the hardware CTA scheduler balances better) and ZPLT_PREFETCH=1
+// (prefetch.global.L2 of the next tile during the transform: 44.9 ms — the extra translations
+// of 1024 distinct 2 MB pages per tile cost more than the prefetch saves).
 template <int N, int T>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *S         = reinterpret_cast<cplx *>(smem_raw);
     constexpr int M = N / 16;
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
-    const long long base = (long long) blockIdx.z * g.astride + (long long) blockIdx.y * g.ostride +
-                           (long long) blockIdx.x * g.tstride + (long long) (p % g.pa) * g.plo_stride +
-                           (long long) (p / g.pa) * g.phi_stride;
-    cplx v[16];
+    const long long poff = (long long) (p % g.pa) * g.plo_stride + (long long) (p / g.pa) * g.phi_stride;
+    const long long ntiles = (long long) g.grid_x * g.grid_y * g.grid_z;
+    auto tile_base = [&](long long t) {
+        const long long tx = t % g.grid_x, ty = (t / g.grid_x) % g.grid_y, tz = t / ((long long) g.grid_x * g.grid_y);
+        return tz * g.astride + ty * g.ostride + tx * g.tstride + poff;
+    };
+    // lanes that lead a contiguous run of the tile issue the prefetches (all lanes for row tiles)
+    const bool pf_lane = (g.plo_stride != 1) || ((p & 7) == 0);
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long base = tile_base(t);
+        cplx v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
-    fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+        for (int e = 0; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
+        if (g.prefetch && t + gridDim.x < ntiles && pf_lane) {
+            const long long nb = tile_base(t + gridDim.x);
 #pragma unroll
-    for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (b + M * e) * g.nstride], v[e]);
+            for (int e = 0; e < 16; e++) prefetch_l2(&data[nb + (long long) (b + M * e) * g.nstride]);
+        }
+        fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+#pragma unroll
+        for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (b + M * e) * g.nstride], v[e]);
+        __syncthreads();  // the exchange buffer is reused by the next tile
+    }
 }
 
 // ------------------------------------------------------------------ generation + x FFT
@@ -525,6 +547,18 @@ int fft_tile_T(int N) {
 }
 size_t fft_tile_smem(int N, int T) { return (size_t) T * (N + 1) * sizeof(cplx); }
 
+// CTAs that fit on the device at once (persistent kernels launch exactly that many)
+static int persistent_ctas(const void *func, int threads, size_t smem) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int k = env_int("ZPLT_CTAS_PER_SM", 0);
+    if (k > 0 && k < per_sm) per_sm = k;
+    return sms * per_sm;
+}
+
 template <int N, int T>
 static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
     size_t smem = fft_tile_smem(N, T);
@@ -534,8 +568,12 @@ static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStr
         int cv = env_int("ZPLT_CARVEOUT", -1);
         if (cv >= 0) cudaFuncSetAttribute(fft_tile_kernel<N, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
     }
-    dim3 grid(g.grid_x, g.grid_y, g.grid_z);
-    fft_tile_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(data, g, tw);
+    const long long ntiles = (long long) g.grid_x * g.grid_y * g.grid_z;
+    long long nctas        = (long long) persistent_ctas((const void *) fft_tile_kernel<N, T>, T * (N / 16), smem);
+    if (nctas > ntiles || env_int("ZPLT_PERSIST", 0) == 0) nctas = ntiles;
+    TileGeom g2 = g;
+    g2.prefetch = env_int("ZPLT_PREFETCH", 0);
+    fft_tile_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(data, g2, tw);
     return (int) cudaGetLastError();
 }
 
