@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Shared-memory bank-conflict simulator for the FFT exchange patterns (16-byte elements, 128-bit
+accesses are served per quarter-warp: 8 lanes, conflict-free iff their 16-byte slots differ mod 8)."""
+import itertools
+import sys
+
+
+def plan(N):
+    M = N // 16
+    R2 = 16 if M >= 16 else M
+    R3 = N // (16 * R2)
+    return M, R2, R3
+
+
+def accesses(N, T):
+    """yield (name, fn(tid)->list of element addresses per instruction) for every exchange instruction."""
+    M, R2, R3 = plan(N)
+    out = []
+    # pass 1 write: S[k*M + b], k=0..15
+    out.append(("p1 write", lambda b, M=M: [k * M + b for k in range(16)]))
+    passes = [(R2, 16)] + ([(R3, 16 * R2)] if R3 > 1 else [])
+    for i, (R, K) in enumerate(passes):
+        L = N // (K * R)
+        NB = 16 // R
+        last = i == len(passes) - 1
+
+        def rd(b, R=R, K=K, L=L, NB=NB, M=M):
+            res = []
+            for j in range(NB):
+                q = b + j * M
+                kk, l = divmod(q, L)
+                for n in range(R):
+                    res.append(kk * (R * L) + n * L + l)
+            return res
+        out.append((f"p{i+2} read", rd))
+        if not last:
+            def wr(b, R=R, K=K, L=L, NB=NB, M=M):
+                res = []
+                for j in range(NB):
+                    q = b + j * M
+                    kk, l = divmod(q, L)
+                    for k in range(R):
+                        res.append((kk + K * k) * L + l)
+                return res
+            out.append((f"p{i+2} write", wr))
+    return out
+
+
+def conflicts(N, T, pstride, swz=lambda a: a):
+    M, _, _ = plan(N)
+    NT = T * M
+    total, ideal = 0, 0
+    detail = []
+    for name, fn in accesses(N, T):
+        lists = {tid: fn(tid // T) for tid in range(NT)}
+        ninstr = len(lists[0])
+        w = 0
+        for q0 in range(0, NT, 8):
+            lanes = list(range(q0, min(q0 + 8, NT)))
+            for i in range(ninstr):
+                banks = {}
+                for tid in lanes:
+                    p = tid % T
+                    slot = p * pstride + swz(lists[tid][i])
+                    banks.setdefault(slot % 8, set()).add(slot)
+                w += max(len(v) for v in banks.values())
+        nq = (NT + 7) // 8
+        detail.append((name, w / (nq * ninstr)))
+        total += w
+        ideal += nq * ninstr
+    return total / ideal, detail
+
+
+if __name__ == "__main__":
+    N = int(sys.argv[1])
+    T = int(sys.argv[2])
+    for ps_off in range(0, 9):
+        r, d = conflicts(N, T, N + ps_off)
+        print(f"N={N} T={T} PSTRIDE=N+{ps_off}: avg wavefronts/ideal {r:.2f}  " + " ".join(f"{n}:{v:.2f}" for n, v in d))
+    # xor swizzle candidates
+    for sh in (2, 3, 4, 5, 6):
+        for ps_off in (0, 1, 2, 4):
+            r, d = conflicts(N, T, N + ps_off, lambda a, sh=sh: a ^ ((a >> sh) & 7))
+            print(f"N={N} T={T} PSTRIDE=N+{ps_off} swz a^((a>>{sh})&7): {r:.2f}  " + " ".join(f"{n}:{v:.2f}" for n, v in d))
+
+
+def search(N, T):
+    best = None
+    for ps_off in range(0, 9):
+        for sh in (0, 1, 2, 3, 4, 5, 6, 7):
+            swz = (lambda a: a) if sh == 0 else (lambda a, sh=sh: a ^ ((a >> sh) & 7))
+            r, d = conflicts(N, T, N + ps_off, swz)
+            if best is None or r < best[0] - 1e-9:
+                best = (r, ps_off, sh)
+    return best

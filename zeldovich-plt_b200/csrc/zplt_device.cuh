@@ -140,39 +140,40 @@ __device__ __forceinline__ void interp_eig(const GenParams &g, int ikx, int iky,
         int cy    = (c & 2) ? hi[1] : lo[1];
         int cz    = (c & 1) ? hi[2] : lo[2];
         double4 v = ld4(((size_t) cx * pe + (size_t) cy) * hp1 + (size_t) cz);
-        // plain multiply-then-add in corner order, as the reference's left-to-right sum
-        acc.x = (c == 0) ? __dmul_rn(w[c], v.x) : __dadd_rn(acc.x, __dmul_rn(w[c], v.x));
-        acc.y = (c == 0) ? __dmul_rn(w[c], v.y) : __dadd_rn(acc.y, __dmul_rn(w[c], v.y));
-        acc.z = (c == 0) ? __dmul_rn(w[c], v.z) : __dadd_rn(acc.z, __dmul_rn(w[c], v.z));
-        acc.w = (c == 0) ? __dmul_rn(w[c], v.w) : __dadd_rn(acc.w, __dmul_rn(w[c], v.w));
+        // the reference's left-to-right corner sum, with fused multiply-adds
+        acc.x = fma(w[c], v.x, acc.x);
+        acc.y = fma(w[c], v.y, acc.y);
+        acc.z = fma(w[c], v.z, acc.z);
+        acc.w = fma(w[c], v.w, acc.w);
     }
     e[0] = acc.x, e[1] = acc.y, e[2] = acc.z, e[3] = acc.w;
 }
 
-// get_eigenmode (reference src/zeldovich.cpp:229-276): e = {vec0, vec1, vec2, val}
-__device__ __forceinline__ void get_eig(const GenParams &g, int kx, int ky, int kz, double e[4]) {
+// get_eigenmode (reference src/zeldovich.cpp:229-276) folded with the amplitude factor of
+// reference :432-434.  The reference forms e.vec = ehat * k2/(k.ehat) and then
+// F,G,H = rescale * i * e.vec * fundamental / (k2*fundamental^2) * D; the integer k2 cancels, so
+//   s_c = rescale * ehat_c / ((k.ehat) * fundamental)          (one division, one reciprocal sqrt)
+// with s = 0 when k = 0 or k.ehat = 0 (the reference's isfinite guard).  ZA: ehat = k, so
+// s_c = rescale * k_c / (k2 * fundamental).  Agreement with the reference's order of roundings ~1e-16.
+__device__ __forceinline__ void eig_factors(const GenParams &g, int kx, int ky, int kz, int n2, double &s0, double &s1,
+                                            double &s2, double &val) {
     if (!g.qPLT) {
-        e[0] = kx, e[1] = ky, e[2] = kz, e[3] = 1.0;
+        const double q = (n2 == 0) ? 0.0 : 1.0 / ((double) n2 * g.fundamental);
+        s0 = kx * q, s1 = ky * q, s2 = kz * q, val = 1.0;
         return;
     }
     int ikx = kx < 0 ? g.N + kx : kx;
     int iky = ky < 0 ? g.N + ky : ky;
     int ikz = kz < 0 ? g.N + kz : kz;
     ikz     = ikz > g.half ? g.N - ikz : ikz;  // stored half-space is +kz
-    double k2 = (double) (kx * kx + ky * ky + kz * kz);
     double eh[4];
     interp_eig(g, ikx, iky, ikz, eh);
     if (kz < 0) eh[2] = -eh[2];
-    double mag = sqrt(eh[0] * eh[0] + eh[1] * eh[1] + eh[2] * eh[2]);
-    eh[0] /= mag;
-    eh[1] /= mag;
-    eh[2] /= mag;
-    double norm = k2 / (kx * eh[0] + ky * eh[1] + kz * eh[2]);
-    if (k2 == 0.0 || !isfinite(norm)) norm = 0.0;
-    e[0] = norm * eh[0];
-    e[1] = norm * eh[1];
-    e[2] = norm * eh[2];
-    e[3] = eh[3];
+    // |ehat| cancels between the normalisation and k2/(k.ehat): s_c = eh_c / ((k.eh) * fundamental)
+    const double dot = kx * eh[0] + ky * eh[1] + kz * eh[2];
+    double q = 1.0 / (dot * g.fundamental);
+    if (n2 == 0 || !isfinite(q)) q = 0.0;
+    s0 = eh[0] * q, s1 = eh[1] * q, s2 = eh[2] * q, val = eh[3];
 }
 
 // Mask of reference src/zeldovich.cpp:350-358.  n2 = kx^2+ky^2+kz^2.
@@ -196,9 +197,10 @@ __device__ __forceinline__ u128 mode_rng_state(const GenParams &g, int x, int y,
 // cgauss<2> (reference src/power_spectrum.cpp:338-359) given the two uniform deviates
 __device__ __forceinline__ void box_muller(const GenParams &g, double P, double u1, double u2, double &Dr, double &Di) {
     double R     = g.fixed_power ? sqrt(P) : sqrt(-P * log(u1));
-    double theta = 2 * 3.14159265358979323846 * u2;
+    // cos/sin(2*pi*u2): sincospi reduces the argument exactly, so this is at least as accurate as
+    // the reference's cos(2*M_PI*theta) and cheaper than a radian-argument sincos
     double sn, cs;
-    sincos(theta, &sn, &cs);
+    sincospi(2.0 * u2, &sn, &cs);
     Dr = R * cs;
     Di = R * sn;
 }
@@ -216,21 +218,18 @@ __device__ __forceinline__ void primary_mode(const GenParams &g, int x, int y, i
     double P  = __ldg(&g.ptab[n2]);
     box_muller(g, P, u1, u2, m.Dr, m.Di);
     if (m.Dr == 0.0 && m.Di == 0.0) return;  // "D != 0." guard (reference src/zeldovich.cpp:403)
-    double k2 = (double) n2 * g.fundamental2;
-    if (k2 == 0.0) k2 = 1.0;
-    double ik2 = 1. / k2;
-    double e[4];
-    get_eig(g, kx, ky, kz, e);
+    double s0, s1, s2, val;
+    eig_factors(g, kx, ky, kz, n2, s0, s1, s2, val);
     double rescale = 1., f = 1.0;
     if (g.qPLT) {
-        f = (sqrt(1. + 24 * e[3] * g.f_cluster) - 1) * .25;
+        f = (sqrt(1. + 24 * val * g.f_cluster) - 1) * .25;
         // pow(a_NL/a0, target_f - f) (reference src/zeldovich.cpp:428) as exp(log(ratio)*(target_f - f)):
         // |exponent| <~ 0.1, so the two agree to a few 1e-16 relative
         if (g.qPLTrescale) rescale = exp(g.log_growth_ratio * (g.target_f - f));
     }
-    m.s0 = rescale * e[0] * g.fundamental * ik2;
-    m.s1 = rescale * e[1] * g.fundamental * ik2;
-    m.s2 = rescale * e[2] * g.fundamental * ik2;
+    m.s0 = rescale * s0;
+    m.s1 = rescale * s1;
+    m.s2 = rescale * s2;
     m.f  = f;
 }
 

@@ -131,13 +131,28 @@ struct FftPlan {
     static constexpr int R2     = (M >= 16) ? 16 : M;      // 1 when N == 16
     static constexpr int R3     = N / (16 * R2);           // 1 when N <= 256
     static constexpr int PASSES = (R2 == 1) ? 1 : ((R3 == 1) ? 2 : 3);
-    static constexpr int PSTRIDE = N + 1;                  // smem elements per pencil (odd -> no bank conflicts across pencils)
+    static constexpr int RLAST  = (PASSES == 1) ? 16 : ((PASSES == 2) ? R2 : R3);
+};
+
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+
+// Shared-memory image of the T pencils a CTA transforms together.  Thread index = slot*T + pencil,
+// 128-bit accesses are served per quarter-warp (8 lanes), conflict-free iff the 8 sixteen-byte
+// slots differ mod 8.  T >= 8: the 8 lanes are 8 pencils of one slot, an odd pencil stride is
+// enough.  T = 4 or 2: a quarter-warp mixes 2 or 4 slots; pencil stride N+2 (N+4) plus an XOR of
+// the low three index bits with bits [log2(last radix) ..] makes every exchange pattern of every
+// pass conflict-free (searched exhaustively by tools/bank_sim.py).
+template <int N, int T>
+struct FftSmem {
+    static constexpr int PSTRIDE = N + (T >= 8 ? 1 : (T == 4 ? 2 : 4));
+    static constexpr int SHIFT   = (T >= 8) ? -1 : ilog2(FftPlan<N>::RLAST);
+    __device__ static __forceinline__ int at(int a) { return SHIFT < 0 ? a : (a ^ ((a >> (SHIFT < 0 ? 0 : SHIFT)) & 7)); }
 };
 
 // One middle/last pass: radix R, K = product of earlier radices, L = N/(K*R).
 // Reads its inputs from the pencil's shared-memory image S (written by the previous pass),
 // leaves the DFT outputs (twiddled unless LAST) in v[j*R + k] for butterfly j = 0..16/R-1.
-template <int N, int R, int K, bool LAST>
+template <int N, int T, int R, int K, bool LAST>
 __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cplx *__restrict__ tw) {
     constexpr int M  = N / 16;
     constexpr int L  = N / (K * R);
@@ -147,7 +162,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
         const int q  = b + j * M;
         const int kk = q / L, l = q % L;
 #pragma unroll
-        for (int n = 0; n < R; n++) v[j * R + n] = S[kk * (R * L) + n * L + l];
+        for (int n = 0; n < R; n++) v[j * R + n] = S[FftSmem<N, T>::at(kk * (R * L) + n * L + l)];
     }
     dft_groups<R>(v);
     if constexpr (!LAST) {
@@ -162,7 +177,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
             for (int k = 0; k < R; k++) {
                 cplx x = v[j * R + k];
                 if (k > 0) x = cmul(x, pw[k]);
-                S[(kk + K * k) * L + l] = x;
+                S[FftSmem<N, T>::at((kk + K * k) * L + l)] = x;
             }
         }
         __syncthreads();
@@ -171,8 +186,8 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
 
 // In-register FFT of one pencil.  v[e] holds x[b + M*e] on entry and X[b + M*e] on exit.
 // Every thread of the CTA must call this (it contains __syncthreads()).  S = this
-// pencil's shared-memory image (FftPlan<N>::PSTRIDE elements), tw = W_N^j table.
-template <int N>
+// pencil's shared-memory image (FftSmem<N,T>::PSTRIDE elements), tw = W_N^j table.
+template <int N, int T>
 __device__ __forceinline__ void fft_pencil(cplx (&v)[16], cplx *S, int b, const cplx *__restrict__ tw) {
     typedef FftPlan<N> P;
     // pass 1: radix 16 over stride M, K = 1, L = M
@@ -185,15 +200,15 @@ __device__ __forceinline__ void fft_pencil(cplx (&v)[16], cplx *S, int b, const 
         for (int k = 0; k < 16; k++) {
             cplx x = v[k];
             if (k > 0) x = cmul(x, pw[k]);
-            S[k * P::M + b] = x;
+            S[FftSmem<N, T>::at(k * P::M + b)] = x;
         }
     }
     __syncthreads();
     if constexpr (P::PASSES == 2) {
-        fft_pass<N, P::R2, 16, true>(v, S, b, tw);
+        fft_pass<N, T, P::R2, 16, true>(v, S, b, tw);
     } else {
-        fft_pass<N, P::R2, 16, false>(v, S, b, tw);
-        fft_pass<N, P::R3, 16 * P::R2, true>(v, S, b, tw);
+        fft_pass<N, T, P::R2, 16, false>(v, S, b, tw);
+        fft_pass<N, T, P::R3, 16 * P::R2, true>(v, S, b, tw);
     }
     // last pass, radix R, butterfly j: v[j*R + k] = X[b + M*(j + (16/R)*k)]  -> reorder to slot order
     constexpr int RL = (P::PASSES == 2) ? P::R2 : P::R3;

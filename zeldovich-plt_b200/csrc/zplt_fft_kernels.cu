@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_k
 #pragma unroll
             for (int e = 0; e < 16; e++) prefetch_l2(&data[nb + (long long) (b + M * e) * g.nstride]);
         }
-        fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+        fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
 #pragma unroll
         for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (b + M * e) * g.nstride], v[e]);
         __syncthreads();  // the exchange buffer is reused by the next tile
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     constexpr int M  = N / 16;
     constexpr int NT = NP * M;
     cplx *S          = reinterpret_cast<cplx *>(smem_raw);
-    double *state    = reinterpret_cast<double *>(smem_raw + (size_t) NP * FftPlan<N>::PSTRIDE * sizeof(cplx));
+    double *state    = reinterpret_cast<double *>(smem_raw + (size_t) NP * FftSmem<N, NP>::PSTRIDE * sizeof(cplx));
     const int na = g.na;
     const int tid = threadIdx.x, p = tid % NP, b = tid / NP;
     constexpr int half = N / 2;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
             if (origin_row && side == 0 && x == 0) val = make_double2(0.0, 0.0);
             v[e] = val;
         }
-        fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+        fft_pencil<N, NP>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);
         const bool live = (side == 0) || has_twin;
         long long row;
         if (sg.G == 1) {
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     cplx v[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
-    fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+    fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
     const int np = N / sg.G;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
@@ -332,7 +332,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
         v[e] = ld_stream(&src[off]);
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
-    fft_pencil<N>(v, S + p * FftPlan<N>::PSTRIDE, b, tw);
+    fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
     if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]
         {
             double var = 0.0, mp = 0.0, mn = 0.0;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     constexpr int M  = N / 16;
     constexpr int NT = T * M;
     cplx *S      = reinterpret_cast<cplx *>(smem_raw);
-    float *keep  = reinterpret_cast<float *>(smem_raw + (size_t) T * FftPlan<N>::PSTRIDE * sizeof(cplx));  // [2][16][NT]
+    float *keep  = reinterpret_cast<float *>(smem_raw + (size_t) T * FftSmem<N, T>::PSTRIDE * sizeof(cplx));  // [2][16][NT]
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     // z_first counts this rank's planes; the particle id carries the global plane index
     const long long zl = z_first + blockIdx.y;
@@ -545,7 +545,7 @@ int fft_tile_T(int N) {
     }
     return 0;
 }
-size_t fft_tile_smem(int N, int T) { return (size_t) T * (N + 1) * sizeof(cplx); }
+size_t fft_tile_smem(int N, int T) { return (size_t) T * (N + (T >= 8 ? 1 : (T == 4 ? 2 : 4))) * sizeof(cplx); }
 
 // CTAs that fit on the device at once (persistent kernels launch exactly that many)
 static int persistent_ctas(const void *func, int threads, size_t smem) {
