@@ -50,7 +50,13 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // switches for experiments: ZPLT_PERSIST=1 (persistent CTAs walking tiles: 36.0 vs 34.6 ms per
 // pass at PPD=1024 — the hardware CTA scheduler balances better) and ZPLT_PREFETCH=1
 // (prefetch.global.L2 of the next tile during the transform: 44.9 ms — the extra translations
-// of 1024 distinct 2 MB pages per tile cost more than the prefetch saves).
+// of 1024 distinct 2 MB pages per tile cost more than the prefetch saves).  ZPLT_PREFETCH=2
+// skips the transform: the bare load/store pattern of the z pass runs in 23.8 ms (5.8 TB/s,
+// 89 % of the measured copy peak) with 128-byte runs and 46.5 ms with 64-byte runs, i.e. the
+// access pattern is not the limit; the ~11 ms on top are the transform's shared-memory
+// exchanges and FP64 work, serialised against the memory phases of a one-CTA-per-SM kernel.
+// A cp.async landing buffer for the next tile was tried too (12/8/4 of 16 elements prefetched:
+// 36.7/34.9/32.4 ms): the extra shared-memory traffic eats what the prefetch gains.
 template <int N, int T>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_k
 #pragma unroll
             for (int e = 0; e < 16; e++) prefetch_l2(&data[nb + (long long) (b + M * e) * g.nstride]);
         }
-        fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
+        if (!(g.prefetch & 2)) fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // bit 1: memory-pattern-only experiment
 #pragma unroll
         for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (b + M * e) * g.nstride], v[e]);
         __syncthreads();  // the exchange buffer is reused by the next tile
