@@ -1,3 +1,6 @@
-for pf in 2; do for tt in 8 4; do for ps in 0 1; do
-echo "copy-only PREFETCH=$pf TILE_T=$tt PERSIST=$ps"; ZPLT_PREFETCH=$pf ZPLT_TILE_T=$tt ZPLT_PERSIST=$ps python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stage_ms'])"
-done; done; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('RVZel', d['ms_per_step'], d['stage_ms'])"
+python bench.py --icformat RVdoubleZel --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('RVdouble', d['ms_per_step'], d['stage_ms'])"
+python bench.py --za --icformat ZelSimple --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ZA ZelSimple', d['ms_per_step'], d['stage_ms'])"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | cut -c1-900

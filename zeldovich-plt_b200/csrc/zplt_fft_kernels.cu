@@ -320,7 +320,7 @@ __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q
 // One packed array A of the tile: load, transform along y, then either park its values or
 // complete record fields.  A is a compile-time constant, the format test is CTA-uniform and
 // sits outside the element loops.
-template <int N, int T, int A, bool SLAB>
+template <int N, int T, int A, bool SLAB, bool RVZEL>
 __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const SlabGeom &sg, int zl, cplx *S, float *keep,
                                            const cplx *__restrict__ tw, const EmitParams &ep, const RecLayout &L,
                                            unsigned char *rec0, long long z, int x,
@@ -328,7 +328,8 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
     constexpr int M  = N / 16;
     constexpr int NT = T * M;
     const int rb = ep.record_bytes, dbl = L.dbl;
-    const bool rvzel = ep.icformat == 1, qplt = ep.qPLT;
+    constexpr bool rvzel = RVZEL;
+    const bool qplt = ep.qPLT;
     const double vn = ep.vnorm;
     cplx v[16];
 #pragma unroll
@@ -339,7 +340,8 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
     fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
-    if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]
+    double *keepd = reinterpret_cast<double *>(keep);  // the same 64 KB seen as [16][NT] doubles (non-RVZel formats)
+    if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]: parked until A1 completes the displacement
         {
             double var = 0.0, mp = 0.0, mn = 0.0;
 #pragma unroll
@@ -357,19 +359,15 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-                unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
-                put(rec, L.off_d[2], v[e].y, dbl);
-                if (!qplt) put(rec, L.off_v[2], v[e].y * vn, dbl);
-            }
+            for (int e = 0; e < 16; e++) keepd[e * NT + tid] = v[e].y;
         }
-    } else if (A == 2) {  // Im = vel[0] -> vel[2]
+    } else if (A == 2) {  // Im = vel[0] -> vel[2]: parked until A3 completes the velocity
         if (rvzel) {
 #pragma unroll
             for (int e = 0; e < 16; e++) keep[(1 * 16 + e) * NT + tid] = (float) v[e].y;
         } else {
 #pragma unroll
-            for (int e = 0; e < 16; e++) put(rec0 + (size_t) (b + M * e) * N * rb, L.off_v[2], v[e].y, dbl);
+            for (int e = 0; e < 16; e++) keepd[e * NT + tid] = v[e].y;
         }
     } else if (A == 1) {  // Re = pos[1] -> displ[1], Im = pos[2] -> displ[0]
         {
@@ -389,26 +387,30 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
-                __stcs(reinterpret_cast<float4 *>(rec),
-                       make_float4(__uint_as_float(w0), __uint_as_float(w1), (float) v[e].y, (float) v[e].x));
+                *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), (float) v[e].y, (float) v[e].x);
                 if (!qplt)
-                    __stcs(reinterpret_cast<float4 *>(rec + 16),
-                           make_float4(keep[(0 * 16 + e) * NT + tid], (float) (v[e].y * vn), (float) (v[e].x * vn),
-                                       keep[(1 * 16 + e) * NT + tid]));
+                    *reinterpret_cast<float4 *>(rec + 16) =
+                       make_float4(keep[(0 * 16 + e) * NT + tid], (float) (v[e].y * vn), (float) (v[e].x * vn),
+                                   keep[(1 * 16 + e) * NT + tid]);
             }
         } else {
+            // ids and the whole displacement (and, without qPLT, the whole velocity) in one burst of
+            // back-to-back stores to consecutive bytes, so that L2 sees complete sectors
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
+                const double pos0 = keepd[e * NT + tid];
                 if (L.off_ijk >= 0)
                     *reinterpret_cast<ushort4 *>(rec + L.off_ijk) =
                        make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
-                put(rec, L.off_d[1], v[e].x, dbl);
                 put(rec, L.off_d[0], v[e].y, dbl);
+                put(rec, L.off_d[1], v[e].x, dbl);
+                put(rec, L.off_d[2], pos0, dbl);
                 if (!qplt) {
-                    put(rec, L.off_v[1], v[e].x * vn, dbl);
                     put(rec, L.off_v[0], v[e].y * vn, dbl);
+                    put(rec, L.off_v[1], v[e].x * vn, dbl);
+                    put(rec, L.off_v[2], pos0 * vn, dbl);
                 }
             }
         }
@@ -417,22 +419,22 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
-                __stcs(reinterpret_cast<float4 *>(rec + 16),
-                       make_float4(keep[(0 * 16 + e) * NT + tid], (float) v[e].y, (float) v[e].x,
-                                   keep[(1 * 16 + e) * NT + tid]));
+                *reinterpret_cast<float4 *>(rec + 16) =
+                   make_float4(keep[(0 * 16 + e) * NT + tid], (float) v[e].y, (float) v[e].x, keep[(1 * 16 + e) * NT + tid]);
             }
         } else {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
-                put(rec, L.off_v[1], v[e].x, dbl);
                 put(rec, L.off_v[0], v[e].y, dbl);
+                put(rec, L.off_v[1], v[e].x, dbl);
+                put(rec, L.off_v[2], keepd[e * NT + tid], dbl);
             }
         }
     }
 }
 
-template <int N, int T, bool SLAB>
+template <int N, int T, bool SLAB, bool RVZEL>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
    fft_emit_strided_kernel(const cplx *__restrict__ cube, SlabGeom sg, long long z_first, EmitParams ep,
                            const cplx *__restrict__ tw) {
@@ -451,11 +453,21 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     const cplx *src    = SLAB ? cube + x : cube + zl * N * (long long) N + x;  // + B2 row offset  |  + a*N3 + y*N
     const RecLayout L  = rec_layout(ep.icformat);
     unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
-    // A0 and A2 first (their values wait in shared memory), then A1 and A3 complete the record halves
-    emit_array<N, T, 0, SLAB>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
-    if (ep.qPLT) emit_array<N, T, 2, SLAB>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-    emit_array<N, T, 1, SLAB>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-    if (ep.qPLT) emit_array<N, T, 3, SLAB>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    if constexpr (RVZEL) {
+        // RVZel: A0 and A2 first (two parked floats), then A1 and A3 complete the two 16-byte halves
+        emit_array<N, T, 0, SLAB, RVZEL>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
+        if (ep.qPLT) emit_array<N, T, 2, SLAB, RVZEL>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+        emit_array<N, T, 1, SLAB, RVZEL>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+        if (ep.qPLT) emit_array<N, T, 3, SLAB, RVZEL>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+    } else {
+        // other formats: one parked double at a time (A0 -> A1 writes the displacement, A2 -> A3 the velocity)
+        emit_array<N, T, 0, SLAB, RVZEL>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
+        emit_array<N, T, 1, SLAB, RVZEL>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+        if (ep.qPLT) {
+            emit_array<N, T, 2, SLAB, RVZEL>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+            emit_array<N, T, 3, SLAB, RVZEL>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+        }
+    }
     __syncthreads();
     if (tid < 7) {
         constexpr int NW = (NT >= 32) ? NT / 32 : NT;
@@ -671,16 +683,19 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long
                                  const cplx *tw, cudaStream_t st, int *launches) {
     size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
     dim3 grid(N / T, (unsigned) nz, 1);
-    cudaError_t e;
-    if (sg.G > 1) {
-        e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return (int) e;
-        fft_emit_strided_kernel<N, T, true><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);
-    } else {
-        e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return (int) e;
-        fft_emit_strided_kernel<N, T, false><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);
+    const bool slab = sg.G > 1, rvzel = ep.icformat == 1;
+#define ZPLT_EMIT_LAUNCH(SL, RV)                                                                                              \
+    {                                                                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T, SL, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int) smem);                                                                     \
+        if (e != cudaSuccess) return (int) e;                                                                                 \
+        fft_emit_strided_kernel<N, T, SL, RV><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);                    \
     }
+    if (slab && rvzel) ZPLT_EMIT_LAUNCH(true, true)
+    else if (slab) ZPLT_EMIT_LAUNCH(true, false)
+    else if (rvzel) ZPLT_EMIT_LAUNCH(false, true)
+    else ZPLT_EMIT_LAUNCH(false, false)
+#undef ZPLT_EMIT_LAUNCH
     if (launches) *launches += 1;
     return (int) cudaGetLastError();
 }
@@ -693,13 +708,9 @@ int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, 
     ZPLT_CASE(launch_emit_strided_t, 64, 32, cube, sg, z_first, nz, ep, tw, st, launches)
     ZPLT_CASE(launch_emit_strided_t, 128, 16, cube, sg, z_first, nz, ep, tw, st, launches)
     ZPLT_CASE(launch_emit_strided_t, 256, 16, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 256, 8, cube, sg, z_first, nz, ep, tw, st, launches)
     ZPLT_CASE(launch_emit_strided_t, 512, 8, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 512, 4, cube, sg, z_first, nz, ep, tw, st, launches)
     ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 1024, 4, cube, sg, z_first, nz, ep, tw, st, launches)
     ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 2048, 2, cube, sg, z_first, nz, ep, tw, st, launches)
     return (int) cudaErrorInvalidValue;
 }
 
