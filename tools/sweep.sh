@@ -1,6 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('RVZel', d['ms_per_step'], d['stage_ms'])"
-python bench.py --icformat RVdoubleZel --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('RVdouble', d['ms_per_step'], d['stage_ms'])"
-python bench.py --za --icformat ZelSimple --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ZA ZelSimple', d['ms_per_step'], d['stage_ms'])"
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | cut -c1-900
+for d in 0 148 296 592 128; do
+pf=$(( d*4 + (d>0 ? 1 : 0) ))
+echo "z-pass prefetch distance $d (flag $pf)"; ZPLT_PREFETCH=$pf python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stage_ms'])"
+done

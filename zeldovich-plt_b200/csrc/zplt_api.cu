@@ -447,6 +447,10 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
     ep.z0           = z0;
     ep.out          = (unsigned char *) device_out;
     ep.stats        = c->stats;
+    {
+        const char *e = getenv("ZPLT_EMIT_PREFETCH");
+        ep.prefetch = e ? atoi(e) : 1;
+    }
     bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
     if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
     CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->sg.G > 1 ? c->cube + c->slab_elems : c->cube, c->sg, z0, nz, ep, c->tw,

@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_k
         cplx v[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
-        if (g.prefetch && t + gridDim.x < ntiles && pf_lane) {
-            const long long nb = tile_base(t + gridDim.x);
+        // prefetch distance: the tile the CTA that follows this one on the SM will load (about one wave
+        // of CTAs ahead); its rows lie in the 2 MB pages this tile has just touched
+        const long long tpf = t + ((g.prefetch >> 2) > 0 ? (g.prefetch >> 2) : (long long) gridDim.x);
+        if ((g.prefetch & 1) && tpf < ntiles && pf_lane) {
+            const long long nb = tile_base(tpf);
 #pragma unroll
             for (int e = 0; e < 16; e++) prefetch_l2(&data[nb + (long long) (b + M * e) * g.nstride]);
         }
@@ -321,7 +324,8 @@ __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q
 // complete record fields.  A is a compile-time constant, the format test is CTA-uniform and
 // sits outside the element loops.
 template <int N, int T, int A, bool SLAB, bool RVZEL>
-__device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const SlabGeom &sg, int zl, cplx *S, float *keep,
+__device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const cplx *__restrict__ next, const SlabGeom &sg, int zl,
+                                           cplx *S, float *keep,
                                            const cplx *__restrict__ tw, const EmitParams &ep, const RecLayout &L,
                                            unsigned char *rec0, long long z, int x,
                                            int tid, int p, int b, bool first, double (*s_red)[8]) {
@@ -337,6 +341,14 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const S
         // single GPU: rows of the [a][z][y][x] cube; slab rank: rows of the exchanged buffer B2
         const long long off = SLAB ? slab_b2_row(sg, A, zl, b + M * e) : (long long) (b + M * e) * N;
         v[e] = ld_stream(&src[off]);
+    }
+    if (!SLAB && next != nullptr && (p & 7) == 0) {
+        // pull the next array's rows of this tile into L2 while this one is transformed (the y stride
+        // stays inside a few 2 MB pages, unlike the z pass where this prefetch costs more than it gains)
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            prefetch_l2(&next[(long long) (b + M * e) * N]);
+        }
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
     fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
@@ -453,21 +465,31 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     const cplx *src    = SLAB ? cube + x : cube + zl * N * (long long) N + x;  // + B2 row offset  |  + a*N3 + y*N
     const RecLayout L  = rec_layout(ep.icformat);
     unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
+    const bool pf = ep.prefetch;
+    const cplx *s0 = src, *s1 = src + N3, *s2 = src + 2 * N3, *s3 = src + 3 * N3;
+#define ZPLT_EA(A, SRC, NEXT, FIRST) \
+    emit_array<N, T, A, SLAB, RVZEL>(SRC, pf ? (NEXT) : nullptr, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, FIRST, s_red)
     if constexpr (RVZEL) {
         // RVZel: A0 and A2 first (two parked floats), then A1 and A3 complete the two 16-byte halves
-        emit_array<N, T, 0, SLAB, RVZEL>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
-        if (ep.qPLT) emit_array<N, T, 2, SLAB, RVZEL>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-        emit_array<N, T, 1, SLAB, RVZEL>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-        if (ep.qPLT) emit_array<N, T, 3, SLAB, RVZEL>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+        if (ep.qPLT) {
+            ZPLT_EA(0, s0, s2, true);
+            ZPLT_EA(2, s2, s1, false);
+            ZPLT_EA(1, s1, s3, false);
+            ZPLT_EA(3, s3, nullptr, false);
+        } else {
+            ZPLT_EA(0, s0, s1, true);
+            ZPLT_EA(1, s1, nullptr, false);
+        }
     } else {
         // other formats: one parked double at a time (A0 -> A1 writes the displacement, A2 -> A3 the velocity)
-        emit_array<N, T, 0, SLAB, RVZEL>(src, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, true, s_red);
-        emit_array<N, T, 1, SLAB, RVZEL>(src + N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+        ZPLT_EA(0, s0, s1, true);
+        ZPLT_EA(1, s1, ep.qPLT ? s2 : nullptr, false);
         if (ep.qPLT) {
-            emit_array<N, T, 2, SLAB, RVZEL>(src + 2 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
-            emit_array<N, T, 3, SLAB, RVZEL>(src + 3 * N3, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, false, s_red);
+            ZPLT_EA(2, s2, s3, false);
+            ZPLT_EA(3, s3, nullptr, false);
         }
     }
+#undef ZPLT_EA
     __syncthreads();
     if (tid < 7) {
         constexpr int NW = (NT >= 32) ? NT / 32 : NT;

@@ -30,6 +30,7 @@ struct EmitParams {
     long long z0;       // first plane of this launch (records are written relative to it)
     unsigned char *out; // records, (z - z0, y, x) order
     double *stats;      // [ZPLT_STAT_SLOTS][8]: sum dens^2, +max[3], -max[3], pad
+    int prefetch;       // L2-prefetch the next packed array of the tile during the transform
 };
 #define ZPLT_STAT_SLOTS 64
 
