@@ -37,7 +37,8 @@ def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
                 ZD_PLT_target_z=repr(float(kw["PLT_target_z"])), InitialRedshift=repr(float(kw["z_initial"])),
                 ZD_f_cluster=repr(float(kw["f_cluster"])), ZD_qPk_fix_to_mean=kw["fixed_power"],
                 ZD_Pk_norm=repr(float(kw["Pk_norm"])), ZD_Pk_smooth=repr(float(kw["Pk_smooth"])),
-                ZD_Pk_scale=repr(float(kw["Pk_scale"])), ICFormat='"%s"' % fmtname,
+                ZD_Pk_scale=repr(float(kw["Pk_scale"])), ICFormat='"%s"' % fmtname, ZD_qonemode=kw.get("qonemode", 0),
+                ZD_one_mode=" ".join(str(v) for v in kw.get("one_mode", (0, 0, 0))),
                 ZD_Pk_filename='"%s"' % os.path.join(tmp, "pk.pow"))
     if kw["Pk_sigma"] > 0:
         over["ZD_Pk_sigma"] = repr(float(kw["Pk_sigma"]))
@@ -331,3 +332,61 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     compare_records(oracle, got, want)
     assert abs(var / wst["density_variance"] - 1) < 1e-10
     assert np.allclose(md, wst["max_disp"], rtol=1e-10)
+
+
+# ---------------------------------------------------------------- option coverage ---
+@pytest.mark.parametrize("case", [
+    dict(ppd=32, qonemode=1, one_mode=(3, 2, -5)),
+    dict(ppd=32, qonemode=1, one_mode=(0, 0, 7), qPLT=1, icformat="RVdoubleZel", eig=16),
+    dict(ppd=64, k_cutoff=2.0, corner_modes=1, icformat="Zeldovich"),
+    dict(ppd=32, corner_modes=1, qPLT=1, qPLTrescale=1, PLT_target_z=2.0, f_cluster=0.9, icformat="RVZel", eig=32),
+    dict(ppd=64, Pk_smooth=2.5, Pk_scale=0.7, icformat="ZelSimple"),
+    dict(ppd=16, icformat="RVdoubleZel"),
+])
+def test_options_full_path(pkg, oracle, case):
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    ctx.generate()
+    got = ctx.fetch_planes(0, kw["ppd"])
+    want, wst = oracle.run(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    compare_records(oracle, got, want)
+    assert abs(ctx.stats()["density_variance"] - wst["density_variance"]) <= 1e-10 * max(wst["density_variance"], 1e-300)
+    ctx.close()
+
+
+def test_power_law_full_path(pkg, oracle):
+    synth = load_synth()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_param(os.path.join(tmp, "c.par"), NP=32**3, ZD_Pk_filename='""', ZD_Pk_powerlaw_index="-1.5", ZD_Pk_sigma=0,
+                          ZD_Pk_sigma_ratio="0.01", ZD_Pk_norm="4.0", ICFormat='"RVdoubleZel"', ZD_Seed=5)
+        P = pkg.Parameters(os.path.join(tmp, "c.par"))
+        power = pkg.PowerSpectrum(P)
+        ctx = pkg.Context(P.config(device=0))
+        power.apply(ctx)
+        ctx.generate()
+        got = ctx.fetch_planes(0, 32)
+        ctx.close()
+    cfg = oracle.make_config(32, seed=5, is_powerlaw=1, powerlaw_index=-1.5, Pk_sigma=0.0, Pk_sigma_ratio=0.01, Pk_norm=4.0,
+                             icformat="RVdoubleZel")
+    want, _ = oracle.run(cfg, None)
+    compare_records(oracle, got, want)
+
+
+def test_cli_qoneslab(pkg, oracle):
+    import subprocess
+
+    synth = load_synth()
+    k, p = helpers.wmap_pk()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_power_table(os.path.join(tmp, "pk.pow"), k, p)
+        synth.write_param(os.path.join(tmp, "c.par"), NP=16**3, ZD_Pk_filename='"pk.pow"', ZD_qoneslab=5, CPD=16)
+        r = subprocess.run([pkg.CLI_PATH, "c.par"], cwd=tmp, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert os.listdir(os.path.join(tmp, "ic_out")) == ["ic_5"]
+        rec = np.fromfile(os.path.join(tmp, "ic_out", "ic_5"), dtype=pkg.RECORD_DTYPES[1])
+    want, _ = oracle.run(oracle.make_config(16), (k, p))
+    compare_records(oracle, rec, want.reshape(16, -1)[5])

@@ -737,3 +737,14 @@ extern "C" int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *
 extern "C" void zplt_set_error_(const char *msg) { g_err = msg ? msg : ""; }
 extern "C" int zplt_ctx_ppd_(const zplt_ctx *c) { return c ? c->N : 0; }
 extern "C" int zplt_ctx_icformat_(const zplt_ctx *c) { return c ? c->cfg.icformat : -1; }
+extern "C" void *zplt_pinned_alloc_(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void zplt_pinned_free_(void *p) {
+    if (p) cudaFreeHost(p);
+}

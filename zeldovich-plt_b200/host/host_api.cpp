@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -194,7 +195,28 @@ struct WriteStats {
     double seconds = 0;
 };
 
-static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, WriteStats *ws) {
+// pinned host staging (device half of the library); falls back to pageable memory if pinning fails
+extern "C" void *zplt_pinned_alloc_(size_t bytes);
+extern "C" void zplt_pinned_free_(void *p);
+
+struct HostBuffer {
+    unsigned char *p = nullptr;
+    bool pinned      = false;
+    explicit HostBuffer(size_t bytes) {
+        p = (unsigned char *) zplt_pinned_alloc_(bytes);
+        pinned = p != nullptr;
+        if (!p) p = (unsigned char *) malloc(bytes);
+    }
+    ~HostBuffer() {
+        if (pinned)
+            zplt_pinned_free_(p);
+        else
+            free(p);
+    }
+};
+
+// qoneslab >= 0: write only that z plane (reference src/zeldovich.cpp:669-682)
+static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, int qoneslab, WriteStats *ws) {
     fs::path dir(output_dir);
     std::error_code ec;
     if (fs::exists(dir, ec)) {
@@ -212,12 +234,18 @@ static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *
     int64_t chunk      = (int64_t) ((512ull << 20) / plane);
     if (chunk < 1) chunk = 1;
     if (chunk > ppd) chunk = ppd;
-    std::vector<unsigned char> buf((size_t) chunk * plane);
+    HostBuffer buf((size_t) chunk * plane);
+    if (!buf.p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host staging", (size_t) chunk * plane);
     int64_t last_file = -1;
     FILE *fp          = nullptr;
-    for (int64_t z0 = 0; z0 < ppd; z0 += chunk) {
-        const int64_t nz = (z0 + chunk <= ppd) ? chunk : ppd - z0;
-        int rc           = zplt_fetch_planes(ctx, z0, nz, buf.data());
+    int64_t zbeg = 0, zend = ppd;
+    if (qoneslab >= 0) {
+        if (qoneslab >= ppd) return ZPLT_OK;  // the reference's loop simply never matches
+        zbeg = qoneslab, zend = qoneslab + 1;
+    }
+    for (int64_t z0 = zbeg; z0 < zend; z0 += chunk) {
+        const int64_t nz = (z0 + chunk <= zend) ? chunk : zend - z0;
+        int rc           = zplt_fetch_planes(ctx, z0, nz, buf.p);
         if (rc) {
             if (fp) fclose(fp);
             return rc;
@@ -233,7 +261,7 @@ static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *
                 last_file = fileno;
                 if (ws) ws->files++;
             }
-            if (fwrite(buf.data() + (size_t) (z - z0) * plane, 1, plane, fp) != plane) {
+            if (fwrite(buf.p + (size_t) (z - z0) * plane, 1, plane, fp) != plane) {
                 fclose(fp);
                 return hfail(ZPLT_EINVAL, "short write on ic file %lld", (long long) fileno);
             }
@@ -251,7 +279,7 @@ extern "C" int zplt_ctx_icformat_(const zplt_ctx *ctx);
 
 extern "C" int zplt_write_ic_files(zplt_ctx *ctx, const char *output_dir, int32_t cpd) {
     if (!ctx || !output_dir) return hfail(ZPLT_EINVAL, "null argument");
-    return write_ic_files(ctx, zplt_ctx_ppd_(ctx), zplt_ctx_icformat_(ctx), output_dir, cpd, nullptr);
+    return write_ic_files(ctx, zplt_ctx_ppd_(ctx), zplt_ctx_icformat_(ctx), output_dir, cpd, -1, nullptr);
 }
 
 // ---------------------------------------------------------------- whole run -------
@@ -294,17 +322,18 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
     if ((rc = zplt_generate(ctx))) return bail(rc);
     WriteStats ws;
     if (write_files) {
-        if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, &ws))) return bail(rc);
+        if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, &ws))) return bail(rc);
     } else {
         // still run the emission (statistics) without keeping the records
         const size_t plane = (size_t) P.ppd * P.ppd * zplt_record_bytes(cfg.icformat);
         int64_t chunk      = (int64_t) ((512ull << 20) / plane);
         if (chunk < 1) chunk = 1;
         if (chunk > P.ppd) chunk = P.ppd;
-        std::vector<unsigned char> buf((size_t) chunk * plane);
+        HostBuffer buf((size_t) chunk * plane);
+        if (!buf.p) return bail(hfail(ZPLT_ENOMEM, "cannot allocate host staging"));
         for (int64_t z0 = 0; z0 < P.ppd; z0 += chunk) {
             int64_t nz = (z0 + chunk <= P.ppd) ? chunk : P.ppd - z0;
-            if ((rc = zplt_fetch_planes(ctx, z0, nz, buf.data()))) return bail(rc);
+            if ((rc = zplt_fetch_planes(ctx, z0, nz, buf.p))) return bail(rc);
         }
     }
     if ((rc = zplt_synchronize(ctx))) return bail(rc);
