@@ -138,6 +138,13 @@ int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32
  * receive buffer (stage 2); -1 if that rank does not hold it. */
 int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray, int32_t stage, int32_t rank, int32_t a, int64_t z, int64_t y);
 
+/* ZD_qdensity (reference src/output.cpp:196,217-224; src/zeldovich.cpp:871-876): the same calls with an
+ * extra float32 density plane per z, `dens = Re A0`, in (z, y, x) order.  Pass a NULL record pointer
+ * for a density-only run (ZD_qdensity = 2: the reference then skips the displacement arrays; here the
+ * records are simply not stored).  Either pointer, not both, may be NULL. */
+int zplt_emit_planes_density(zplt_ctx *ctx, int64_t z0, int64_t nz, void *device_out, float *device_density);
+int zplt_fetch_planes_density(zplt_ctx *ctx, int64_t z0, int64_t nz, void *host_out, float *host_density);
+
 /* Reset the statistics accumulated by the emit calls. */
 int zplt_reset_stats(zplt_ctx *ctx);
 /* density_variance = sum over emitted particles of dens^2; max_disp[j] = signed value of
@@ -213,6 +220,11 @@ int zplt_load_eigenmodes_file(zplt_ctx *ctx, const char *path);
  * src/zeldovich.cpp:667-682): remove stale ic_* / zeldovich.* files, then append plane z to
  * `output_dir/ic_{z*cpd/ppd}` in ascending z.  Needs zplt_generate to have run. */
 int zplt_write_ic_files(zplt_ctx *ctx, const char *output_dir, int32_t cpd);
+/* The same with the ZD_qdensity options: qdensity 0 = records only, 1 = records + `density_path` (float32 planes,
+ * ascending z, opened "wb" as the reference does in InitOutputBuffers, src/output.cpp:282-288), 2 = density only;
+ * qoneslab >= 0 writes just that plane (reference src/zeldovich.cpp:669). */
+int zplt_write_outputs(zplt_ctx *ctx, const char *output_dir, int32_t cpd, int32_t qdensity, const char *density_path,
+                       int32_t qoneslab);
 
 /* What `zeldovich <param_file>` does end to end (reference main, src/zeldovich.cpp:848-1032);
  * the report carries the numbers the reference prints on stderr. */

@@ -390,3 +390,35 @@ def test_cli_qoneslab(pkg, oracle):
         rec = np.fromfile(os.path.join(tmp, "ic_out", "ic_5"), dtype=pkg.RECORD_DTYPES[1])
     want, _ = oracle.run(oracle.make_config(16), (k, p))
     compare_records(oracle, rec, want.reshape(16, -1)[5])
+
+
+def test_density_planes_qdensity(pkg, oracle):
+    """ZD_qdensity: float32 Re(A0) planes next to (1) or instead of (2) the records, through API and CLI."""
+    import subprocess
+
+    synth = load_synth()
+    kw = default_kw(ppd=32, icformat="RVZel")
+    pk = helpers.wmap_pk()
+    ctx, P, power = make_ctx(pkg, kw, pk, None)
+    ctx.generate()
+    rec, dens = ctx.fetch_planes_density(0, 32)
+    _, dens_only = ctx.fetch_planes_density(3, 5, records=False)
+    ctx.close()
+    cube = oracle.fft3_backward(oracle.spectral_cube(oracle.make_config(**kw), pk))
+    want = cube[0].real
+    assert np.max(np.abs(dens - want.astype(np.float32))) <= 2e-7 * np.max(np.abs(want))
+    assert np.array_equal(dens_only, dens[3:8])
+    wrec, _ = oracle.run(oracle.make_config(**kw), pk)
+    compare_records(oracle, rec, wrec)
+    for qd in (1, 2):
+        with tempfile.TemporaryDirectory() as tmp:
+            synth.write_power_table(os.path.join(tmp, "pk.pow"), pk[0], pk[1])
+            synth.write_param(os.path.join(tmp, "c.par"), NP=32**3, ZD_Pk_filename='"pk.pow"', ZD_qdensity=qd)
+            r = subprocess.run([pkg.CLI_PATH, "c.par"], cwd=tmp, stderr=subprocess.PIPE, text=True)
+            assert r.returncode == 0, r.stderr
+            files = sorted(os.listdir(os.path.join(tmp, "ic_out")))
+            assert "density32" in files
+            assert (len(files) == 1) == (qd == 2)  # qdensity = 2 writes no ic_* files
+            d = np.fromfile(os.path.join(tmp, "ic_out", "density32"), dtype=np.float32).reshape(32, 32, 32)
+            assert np.array_equal(d, dens)
+            assert ("maximum component-wise" in r.stderr) == (qd == 1)

@@ -88,7 +88,8 @@ class RunReport(C.Structure):
 EXPORTS = [
     "zplt_create", "zplt_destroy", "zplt_last_error", "zplt_record_bytes", "zplt_narray", "zplt_set_power_spline",
     "zplt_set_power_law", "zplt_set_eigenmodes", "zplt_workspace_bytes", "zplt_set_workspace", "zplt_set_stream",
-    "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
+    "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_emit_planes_density", "zplt_fetch_planes_density",
+    "zplt_write_outputs", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
     "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
@@ -124,6 +125,9 @@ def lib():
     L.zplt_generate.argtypes = [vp]
     L.zplt_emit_planes.argtypes = [vp, i64, i64, vp]
     L.zplt_fetch_planes.argtypes = [vp, i64, i64, vp]
+    L.zplt_emit_planes_density.argtypes = [vp, i64, i64, vp, vp]
+    L.zplt_fetch_planes_density.argtypes = [vp, i64, i64, vp, vp]
+    L.zplt_write_outputs.argtypes = [vp, C.c_char_p, i32, i32, C.c_char_p, i32]
     L.zplt_reset_stats.argtypes = [vp]
     L.zplt_get_stats.argtypes = [vp, dp, dp]
     L.zplt_synchronize.argtypes = [vp]
@@ -313,6 +317,15 @@ class Context:
         assert out.nbytes >= n * self.record_bytes
         _ck(lib().zplt_fetch_planes(self._h, z0, nz, C.c_void_p(out.ctypes.data)))
         return out
+
+    def fetch_planes_density(self, z0, nz, records=True):
+        """(records or None, float32 density [nz, ppd, ppd]) of planes z0..z0+nz-1 (ZD_qdensity)."""
+        n = nz * self.ppd * self.ppd
+        rec = np.empty(n, dtype=self.record_dtype) if records else None
+        dens = np.empty(n, dtype=np.float32)
+        _ck(lib().zplt_fetch_planes_density(self._h, z0, nz, C.c_void_p(rec.ctypes.data) if records else None,
+                                            C.c_void_p(dens.ctypes.data)))
+        return rec, dens.reshape(nz, self.ppd, self.ppd)
 
     def fetch_planes_ptr(self, z0, nz, host_ptr):
         _ck(lib().zplt_fetch_planes(self._h, z0, nz, C.c_void_p(host_ptr)))

@@ -432,7 +432,11 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
 extern "C" int zplt_generate(zplt_ctx *c) { return run_generate(c, true); }
 
 extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *device_out) {
-    if (!c || !device_out) return fail(ZPLT_EINVAL, "null argument");
+    return zplt_emit_planes_density(c, z0, nz, device_out, nullptr);
+}
+
+extern "C" int zplt_emit_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, void *device_out, float *device_density) {
+    if (!c || (!device_out && !device_density)) return fail(ZPLT_EINVAL, "null argument");
     if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
     const int nplanes = c->N / c->sg.G;  // planes this rank owns (all of them on a single GPU)
     if (z0 < 0 || nz <= 0 || z0 + nz > nplanes) return fail(ZPLT_EINVAL, "plane range [%lld,%lld) outside [0,%d)", (long long) z0, (long long) (z0 + nz), nplanes);
@@ -446,6 +450,7 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
     ep.vnorm        = c->vnorm;
     ep.z0           = z0;
     ep.out          = (unsigned char *) device_out;
+    ep.dens         = device_density;
     ep.stats        = c->stats;
     {
         const char *e = getenv("ZPLT_EMIT_PREFETCH");
@@ -463,33 +468,44 @@ extern "C" int zplt_emit_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *devic
 }
 
 extern "C" int zplt_fetch_planes(zplt_ctx *c, int64_t z0, int64_t nz, void *host_out) {
-    if (!c || !host_out) return fail(ZPLT_EINVAL, "null argument");
+    return zplt_fetch_planes_density(c, z0, nz, host_out, nullptr);
+}
+
+extern "C" int zplt_fetch_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, void *host_out, float *host_density) {
+    if (!c || (!host_out && !host_density)) return fail(ZPLT_EINVAL, "null argument");
     if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
     if (z0 < 0 || nz <= 0 || z0 + nz > c->N / c->sg.G) return fail(ZPLT_EINVAL, "plane range outside this rank's planes");
     CK(cudaSetDevice(c->device));
-    const size_t plane = (size_t) c->N * c->N * zplt_record_bytes(c->cfg.icformat);
-    long long chunk    = (long long) ((256ull << 20) / plane);
+    const size_t plane  = (size_t) c->N * c->N * zplt_record_bytes(c->cfg.icformat);
+    const size_t dplane = (size_t) c->N * c->N * sizeof(float);
+    long long chunk     = (long long) ((256ull << 20) / plane);
     if (chunk < 1) chunk = 1;
     if (chunk > nz) chunk = nz;
-    if (c->stage_bytes < (size_t) chunk * plane) {
+    // each staging buffer holds `chunk` planes of records followed by `chunk` planes of density
+    if (c->stage_bytes < (size_t) chunk * (plane + dplane)) {
         for (int i = 0; i < 2; i++) {
             if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
             c->stage_dev[i] = nullptr;
-            CK(cudaMalloc((void **) &c->stage_dev[i], (size_t) chunk * plane));
+            CK(cudaMalloc((void **) &c->stage_dev[i], (size_t) chunk * (plane + dplane)));
         }
-        c->stage_bytes = (size_t) chunk * plane;
+        c->stage_bytes = (size_t) chunk * (plane + dplane);
     }
     int i = 0;
     bool used[2] = {false, false};
     for (long long z = z0; z < z0 + nz; z += chunk, i ^= 1) {
         long long n = (z + chunk <= z0 + nz) ? chunk : (z0 + nz - z);
         if (used[i]) CK(cudaStreamWaitEvent(c->stream, c->stage_free[i], 0));
-        int rc = zplt_emit_planes(c, z, n, c->stage_dev[i]);
+        float *ddev = host_density ? (float *) (c->stage_dev[i] + (size_t) chunk * plane) : nullptr;
+        int rc = zplt_emit_planes_density(c, z, n, host_out ? c->stage_dev[i] : nullptr, ddev);
         if (rc) return rc;
         CK(cudaEventRecord(c->stage_full[i], c->stream));
         CK(cudaStreamWaitEvent(c->copy_stream, c->stage_full[i], 0));
-        CK(cudaMemcpyAsync((unsigned char *) host_out + (size_t) (z - z0) * plane, c->stage_dev[i], (size_t) n * plane,
-                           cudaMemcpyDeviceToHost, c->copy_stream));
+        if (host_out)
+            CK(cudaMemcpyAsync((unsigned char *) host_out + (size_t) (z - z0) * plane, c->stage_dev[i], (size_t) n * plane,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
+        if (host_density)
+            CK(cudaMemcpyAsync(host_density + (size_t) (z - z0) * c->N * c->N, ddev, (size_t) n * dplane, cudaMemcpyDeviceToHost,
+                               c->copy_stream));
         CK(cudaEventRecord(c->stage_free[i], c->copy_stream));
         used[i] = true;
     }

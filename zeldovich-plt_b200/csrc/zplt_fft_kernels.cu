@@ -363,6 +363,11 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
             }
             fold_stats<NT>(s_red, tid, var, 0, mp, 1, mn, 4);
         }
+        if (ep.dens != nullptr) {  // density planes (reference src/output.cpp:196,217-224): float(Re A0)
+            float *dp = ep.dens + ((size_t) (zl - ep.z0) * N) * N + x;
+#pragma unroll
+            for (int e = 0; e < 16; e++) dp[(size_t) (b + M * e) * N] = (float) v[e].x;
+        }
         if (rvzel) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
@@ -392,7 +397,9 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
             fold_stats<NT>(s_red, tid, mp1, 2, mn1, 5, mp2, 3);
             fold_stats<NT>(s_red, tid, mn2, 6, 0.0, 7, 0.0, 7);
         }
-        if (rvzel) {
+        if (ep.out == nullptr) {
+            // density-only run: nothing to store
+        } else if (rvzel) {
             const unsigned int w1 = (unsigned int) (unsigned short) x;
 #pragma unroll
             for (int e = 0; e < 16; e++) {
@@ -427,7 +434,8 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
             }
         }
     } else {  // A == 3: Re = vel[1] -> vel[1], Im = vel[2] -> vel[0]
-        if (rvzel) {
+        if (ep.out == nullptr) {
+        } else if (rvzel) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;

@@ -28,7 +28,8 @@ struct EmitParams {
     int qPLT;
     double vnorm;       // velocity factor when !qPLT (reference src/output.cpp:78-82)
     long long z0;       // first plane of this launch (records are written relative to it)
-    unsigned char *out; // records, (z - z0, y, x) order
+    unsigned char *out; // records, (z - z0, y, x) order; NULL: no records (ZD_qdensity = 2)
+    float *dens;        // optional density planes, float32, (z - z0, y, x) order (ZD_qdensity); NULL: none
     double *stats;      // [ZPLT_STAT_SLOTS][8]: sum dens^2, +max[3], -max[3], pad
     int prefetch;       // L2-prefetch the next packed array of the tile during the transform
 };

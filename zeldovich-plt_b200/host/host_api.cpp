@@ -77,7 +77,7 @@ extern "C" int zplt_config_from_params(const zplt_params *p, zplt_config *c) {
     int fmt = zplt_icformat_code(p->ICFormat);
     if (fmt < 0) return hfail(ZPLT_EINVAL, "Error: unknown ICFormat \"%s\". Aborting.", p->ICFormat);
     if (p->f_NL != 0.) return hfail(ZPLT_EINVAL, "ZD_f_NL != 0 (primordial non-Gaussianity) is outside the B200 hot path");
-    if (p->qdensity != 0) return hfail(ZPLT_EINVAL, "ZD_qdensity output is not built yet");
+    if (p->qdensity < 0 || p->qdensity > 2) return hfail(ZPLT_EINVAL, "ZD_qdensity must be 0, 1 or 2");
     c->ppd          = p->ppd;
     c->boxsize      = p->boxsize;
     c->seed         = (int64_t) p->seed;  // int -> unsigned long sign-extends (reference src/power_spectrum.cpp:14)
@@ -216,7 +216,8 @@ struct HostBuffer {
 };
 
 // qoneslab >= 0: write only that z plane (reference src/zeldovich.cpp:669-682)
-static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, int qoneslab, WriteStats *ws) {
+static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, int qoneslab, WriteStats *ws,
+                          int qdensity = 0, const char *density_path = nullptr) {
     fs::path dir(output_dir);
     std::error_code ec;
     if (fs::exists(dir, ec)) {
@@ -236,6 +237,16 @@ static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *
     if (chunk > ppd) chunk = ppd;
     HostBuffer buf((size_t) chunk * plane);
     if (!buf.p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host staging", (size_t) chunk * plane);
+    // ZD_qdensity: float32 density planes appended to one file, opened "wb" (reference src/output.cpp:282-288)
+    const size_t dplane = (size_t) ppd * ppd * sizeof(float);
+    HostBuffer dbuf(qdensity ? (size_t) chunk * dplane : 16);
+    FILE *densfp = nullptr;
+    if (qdensity) {
+        if (!density_path) return hfail(ZPLT_EINVAL, "ZD_qdensity needs a density file name");
+        densfp = fopen(density_path, "wb");
+        if (!densfp) return hfail(ZPLT_EINVAL, "cannot open density file \"%s\"", density_path);
+    }
+    const bool records = qdensity != 2;
     int64_t last_file = -1;
     FILE *fp          = nullptr;
     int64_t zbeg = 0, zend = ppd;
@@ -245,13 +256,21 @@ static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *
     }
     for (int64_t z0 = zbeg; z0 < zend; z0 += chunk) {
         const int64_t nz = (z0 + chunk <= zend) ? chunk : zend - z0;
-        int rc           = zplt_fetch_planes(ctx, z0, nz, buf.p);
+        int rc           = zplt_fetch_planes_density(ctx, z0, nz, records ? buf.p : nullptr, qdensity ? (float *) dbuf.p : nullptr);
         if (rc) {
             if (fp) fclose(fp);
+            if (densfp) fclose(densfp);
             return rc;
         }
         const double t0 = now_s();
-        for (int64_t z = z0; z < z0 + nz; z++) {
+        if (densfp) {
+            if (fwrite(dbuf.p, 1, (size_t) nz * dplane, densfp) != (size_t) nz * dplane) {
+                fclose(densfp);
+                return hfail(ZPLT_EINVAL, "short write on the density file");
+            }
+            if (ws) ws->bytes += (int64_t) ((size_t) nz * dplane);
+        }
+        for (int64_t z = z0; records && z < z0 + nz; z++) {
             const int64_t fileno = z * cpd / ppd;  // integer division, reference src/output.cpp:208
             if (fileno != last_file) {
                 if (fp) fclose(fp);
@@ -270,6 +289,7 @@ static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *
         if (ws) ws->seconds += now_s() - t0;
     }
     if (fp) fclose(fp);
+    if (densfp) fclose(densfp);
     return ZPLT_OK;
 }
 
@@ -280,6 +300,20 @@ extern "C" int zplt_ctx_icformat_(const zplt_ctx *ctx);
 extern "C" int zplt_write_ic_files(zplt_ctx *ctx, const char *output_dir, int32_t cpd) {
     if (!ctx || !output_dir) return hfail(ZPLT_EINVAL, "null argument");
     return write_ic_files(ctx, zplt_ctx_ppd_(ctx), zplt_ctx_icformat_(ctx), output_dir, cpd, -1, nullptr);
+}
+
+extern "C" int zplt_write_outputs(zplt_ctx *ctx, const char *output_dir, int32_t cpd, int32_t qdensity, const char *density_path,
+                                  int32_t qoneslab) {
+    if (!ctx || !output_dir) return hfail(ZPLT_EINVAL, "null argument");
+    return write_ic_files(ctx, zplt_ctx_ppd_(ctx), zplt_ctx_icformat_(ctx), output_dir, cpd, qoneslab, nullptr, qdensity, density_path);
+}
+
+// density file name: ZD_density_filename with "{:d}" replaced by ppd (reference src/output.cpp:283, default "density{:d}")
+static std::string density_path_of(const zplt_params &P) {
+    std::string name = P.density_filename;
+    const size_t pos = name.find("{:d}");
+    if (pos != std::string::npos) name.replace(pos, 4, std::to_string((long long) P.ppd));
+    return (fs::path(P.output_dir) / name).string();
 }
 
 // ---------------------------------------------------------------- whole run -------
@@ -322,7 +356,9 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
     if ((rc = zplt_generate(ctx))) return bail(rc);
     WriteStats ws;
     if (write_files) {
-        if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, &ws))) return bail(rc);
+        if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, &ws, P.qdensity,
+                                 P.qdensity ? density_path_of(P).c_str() : nullptr)))
+            return bail(rc);
     } else {
         // still run the emission (statistics) without keeping the records
         const size_t plane = (size_t) P.ppd * P.ppd * zplt_record_bytes(cfg.icformat);
@@ -352,11 +388,13 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
     fprintf(stderr, "The rms density variation of the pixels is %f\n", rep->rms_density);
     rep->sigma_prediction = zplt_power_sigmaR(pk, P.separation / 4.0) * pow(P.boxsize, 1.5);
     fprintf(stderr, "This could be compared to the P(k) prediction of %f\n", rep->sigma_prediction);
-    fprintf(stderr, "The maximum component-wise displacements are (%g, %g, %g), same units as BoxSize.\n", rep->max_disp[0],
-            rep->max_disp[1], rep->max_disp[2]);
-    fprintf(stderr,
-            "For Abacus' 2LPT implementation to work (assuming FINISH_WAIT_RADIUS = 1),\n\tthis implies a maximum CPD of %d\n",
-            (int) (P.boxsize / (2 * fabs(rep->max_disp[2]))));
+    if (P.qdensity != 2) {  // reference src/zeldovich.cpp:998
+        fprintf(stderr, "The maximum component-wise displacements are (%g, %g, %g), same units as BoxSize.\n", rep->max_disp[0],
+                rep->max_disp[1], rep->max_disp[2]);
+        fprintf(stderr,
+                "For Abacus' 2LPT implementation to work (assuming FINISH_WAIT_RADIUS = 1),\n\tthis implies a maximum CPD of %d\n",
+                (int) (P.boxsize / (2 * fabs(rep->max_disp[2]))));
+    }
     fprintf(stderr, "Device stages: generate %.3f ms, z-FFT %.3f ms, y-FFT %.3f ms, x-FFT+emit %.3f ms\n", tm[0], tm[1], tm[2], tm[3]);
     if (write_files)
         fprintf(stderr, "Writing ic files took %.3g sec to write %.3g MB ==> %.3g MB/sec\n", ws.seconds, ws.bytes / 1e6,
