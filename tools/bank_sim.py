@@ -13,36 +13,38 @@ def plan(N):
 
 
 def accesses(N, T):
-    """yield (name, fn(tid)->list of element addresses per instruction) for every exchange instruction."""
-    M, R2, R3 = plan(N)
-    out = []
-    # pass 1 write: S[k*M + b], k=0..15
-    out.append(("p1 write", lambda b, M=M: [k * M + b for k in range(16)]))
-    passes = [(R2, 16)] + ([(R3, 16 * R2)] if R3 > 1 else [])
-    for i, (R, K) in enumerate(passes):
-        L = N // (K * R)
-        NB = 16 // R
-        last = i == len(passes) - 1
+    """(name, fn(slot b) -> element addresses, one per exchange instruction) for the kernel's passes.
 
-        def rd(b, R=R, K=K, L=L, NB=NB, M=M):
+    3-pass plans: pass 2 works in place on each thread's own 16 locations and pass 3 only reads what
+    the R3 neighbouring slots (same warp) wrote — see fft_pencil in csrc/zplt_fft.cuh."""
+    M, R2, R3 = plan(N)
+    out = [("p1 write", lambda b, M=M: [k * M + b for k in range(16)])]
+    if R3 == 1:
+        L, NB = 1, 16 // R2
+
+        def rd(b, R=R2, NB=NB, M=M):
             res = []
             for j in range(NB):
                 q = b + j * M
-                kk, l = divmod(q, L)
                 for n in range(R):
-                    res.append(kk * (R * L) + n * L + l)
+                    res.append(q * R + n)
             return res
-        out.append((f"p{i+2} read", rd))
-        if not last:
-            def wr(b, R=R, K=K, L=L, NB=NB, M=M):
-                res = []
-                for j in range(NB):
-                    q = b + j * M
-                    kk, l = divmod(q, L)
-                    for k in range(R):
-                        res.append((kk + K * k) * L + l)
-                return res
-            out.append((f"p{i+2} write", wr))
+        out.append(("p2 read", rd))
+        return out
+
+    def p2(b, R3=R3):
+        k1, i = divmod(b, R3)
+        return [k1 * 16 * R3 + n * R3 + i for n in range(16)]
+    out.append(("p2 read/write", p2))
+
+    def p3(b, R3=R3):
+        k1, i = divmod(b, R3)
+        res = []
+        for j in range(16 // R3):
+            for n in range(R3):
+                res.append(k1 * 16 * R3 + (i + R3 * j) * R3 + n)
+        return res
+    out.append(("p3 read", p3))
     return out
 
 

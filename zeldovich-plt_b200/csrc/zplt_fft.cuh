@@ -184,45 +184,86 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
     }
 }
 
-// In-register FFT of one pencil.  v[e] holds x[b + M*e] on entry and X[b + M*e] on exit.
-// Every thread of the CTA must call this (it contains __syncthreads()).  S = this
-// pencil's shared-memory image (FftSmem<N,T>::PSTRIDE elements), tw = W_N^j table.
-template <int N, int T>
-__device__ __forceinline__ void fft_pencil(cplx (&v)[16], cplx *S, int b, const cplx *__restrict__ tw) {
+// In-register FFT of one pencil.  v[e] holds x[b + M*e] on entry and X[bo + M*e] on exit, where
+// bo is the returned output slot (bo == b except for 3-pass lengths, where it is a permutation of
+// the slots — callers use it for every index derived from the transformed data).
+// Every thread of the CTA must call this (it contains __syncthreads()).  S = this pencil's
+// shared-memory image (FftSmem<N,T>::PSTRIDE elements), tw = W_N^j table.
+//
+// 3-pass lengths (N >= 512, radices 16, 16, R3): only the first exchange is a transpose across
+// the whole pencil (CTA barrier).  Pass 2 reads 16 locations and, after its DFT and twiddle, writes
+// its results back to the very same locations; pass 3 then only needs what the R3 neighbouring
+// slots of the same warp wrote, so a __syncwarp() replaces the two CTA barriers of the second
+// exchange and the warps of a CTA drift apart (FP64 and shared-memory phases overlap).
+// WL = false keeps the natural output order (bo == b) at the price of two more CTA barriers: the
+// contiguous-row kernel needs it, because the slot permutation would break its coalesced row stores.
+template <int N, int T, bool WL = true>
+__device__ __forceinline__ int fft_pencil(cplx (&v)[16], cplx *S, int b, const cplx *__restrict__ tw) {
     typedef FftPlan<N> P;
+    typedef FftSmem<N, T> SM;
+    int bo = b;
     // pass 1: radix 16 over stride M, K = 1, L = M
     dft16(v);
     if constexpr (P::PASSES > 1) {
-    {
-        cplx pw[16];
-        twiddle_powers<16>(__ldg(&tw[b]), pw);
+        {
+            cplx pw[16];
+            twiddle_powers<16>(__ldg(&tw[b]), pw);
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            cplx x = v[k];
-            if (k > 0) x = cmul(x, pw[k]);
-            S[FftSmem<N, T>::at(k * P::M + b)] = x;
+            for (int k = 0; k < 16; k++) {
+                cplx x = v[k];
+                if (k > 0) x = cmul(x, pw[k]);
+                S[SM::at(k * P::M + b)] = x;
+            }
         }
-    }
-    __syncthreads();
-    if constexpr (P::PASSES == 2) {
-        fft_pass<N, T, P::R2, 16, true>(v, S, b, tw);
-    } else {
-        fft_pass<N, T, P::R2, 16, false>(v, S, b, tw);
-        fft_pass<N, T, P::R3, 16 * P::R2, true>(v, S, b, tw);
-    }
-    // last pass, radix R, butterfly j: v[j*R + k] = X[b + M*(j + (16/R)*k)]  -> reorder to slot order
-    constexpr int RL = (P::PASSES == 2) ? P::R2 : P::R3;
-    constexpr int NB = 16 / RL;
-    if constexpr (NB > 1) {
-        cplx t[16];
+        __syncthreads();
+        if constexpr (P::PASSES == 2) {
+            fft_pass<N, T, P::R2, 16, true>(v, S, b, tw);
+        } else if constexpr (!WL) {
+            fft_pass<N, T, P::R2, 16, false>(v, S, b, tw);
+            fft_pass<N, T, P::R3, 16 * P::R2, true>(v, S, b, tw);
+        } else {
+            constexpr int R3 = P::R3;
+            static_assert(P::R2 == 16 && R3 * T <= 32 && 32 % (R3 * T) == 0, "pass-3 partners must share a warp");
+            const int k1 = b / R3, i = b % R3;
+            const int base = k1 * (16 * R3);
+            // pass 2: radix 16 over stride R3, in place on this thread's own 16 locations
 #pragma unroll
-        for (int j = 0; j < NB; j++)
+            for (int n = 0; n < 16; n++) v[n] = S[SM::at(base + n * R3 + i)];
+            dft16(v);
+            {
+                cplx pw[16];
+                twiddle_powers<16>(__ldg(&tw[16 * i]), pw);
 #pragma unroll
-            for (int k = 0; k < RL; k++) t[j + NB * k] = v[j * RL + k];
+                for (int k = 0; k < 16; k++) {
+                    cplx x = v[k];
+                    if (k > 0) x = cmul(x, pw[k]);
+                    S[SM::at(base + k * R3 + i)] = x;
+                }
+            }
+            __syncwarp();
+            // pass 3: radix R3 butterflies k2 = i + R3*j of this slot group
+            constexpr int NB3 = 16 / R3;
 #pragma unroll
-        for (int e = 0; e < 16; e++) v[e] = t[e];
-    }
+            for (int j = 0; j < NB3; j++)
+#pragma unroll
+                for (int n = 0; n < R3; n++) v[j * R3 + n] = S[SM::at(base + (i + R3 * j) * R3 + n)];
+            dft_groups<R3>(v);
+            bo = k1 + 16 * i;
+        }
+        // last pass, radix R, butterfly j: v[j*R + k] = X[bo + M*(j + (16/R)*k)]  -> reorder to slot order
+        constexpr int RL = (P::PASSES == 2) ? P::R2 : P::R3;
+        constexpr int NB = 16 / RL;
+        if constexpr (NB > 1) {
+            cplx t[16];
+#pragma unroll
+            for (int j = 0; j < NB; j++)
+#pragma unroll
+                for (int k = 0; k < RL; k++) t[j + NB * k] = v[j * RL + k];
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] = t[e];
+        }
     }  // PASSES > 1
+    return bo;
 }
 
 }  // namespace zplt

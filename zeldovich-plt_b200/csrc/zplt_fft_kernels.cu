@@ -84,9 +84,10 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_k
 #pragma unroll
             for (int e = 0; e < 16; e++) prefetch_l2(&data[nb + (long long) (b + M * e) * g.nstride]);
         }
-        if (!(g.prefetch & 2)) fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // bit 1: memory-pattern-only experiment
+        int bo = b;
+        if (!(g.prefetch & 2)) bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // bit 1: memory-pattern-only experiment
 #pragma unroll
-        for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (b + M * e) * g.nstride], v[e]);
+        for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (bo + M * e) * g.nstride], v[e]);
         __syncthreads();  // the exchange buffer is reused by the next tile
     }
 }
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
             if (origin_row && side == 0 && x == 0) val = make_double2(0.0, 0.0);
             v[e] = val;
         }
-        fft_pencil<N, NP>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);
+        const int bo = fft_pencil<N, NP, false>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);  // natural order: whole rows are stored
         const bool live = (side == 0) || has_twin;
         long long row;
         if (sg.G == 1) {
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
         }
         if (live) {
 #pragma unroll
-            for (int e = 0; e < 16; e++) st_stream(&cube[row + b + M * e], v[e]);
+            for (int e = 0; e < 16; e++) st_stream(&cube[row + bo + M * e], v[e]);
         }
         if (rnd + 1 < rounds) __syncthreads();  // the exchange buffer is reused by the next round
     }
@@ -218,11 +219,11 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     cplx v[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
-    fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
+    const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
     const int np = N / sg.G;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int z = b + M * e, r = z / np, zl = z % np;
+        const int z = bo + M * e, r = z / np, zl = z % np;
         st_stream(&peers.recv[r][(((long long) sg.rank * np + zl) * rows + row) * N + x], v[e]);
     }
 }
@@ -351,7 +352,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
         }
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
-    fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
+    b = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // from here on b is the OUTPUT slot
     double *keepd = reinterpret_cast<double *>(keep);  // the same 64 KB seen as [16][NT] doubles (non-RVZel formats)
     if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]: parked until A1 completes the displacement
         {
