@@ -325,8 +325,13 @@ def main_b200(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         plane = N * N * rb
-        chunk = max(1, min(nloc, (2 << 30) // plane))
-        pinned = torch.empty(chunk * plane, dtype=torch.uint8, pin_memory=True)
+        # one pinned host buffer for all of this rank's records when it is affordable (<= 40 GB), else 2 GiB chunks
+        chunk = nloc if nloc * plane <= (40 << 30) else max(1, min(nloc, (2 << 30) // plane))
+        try:
+            pinned = torch.empty(chunk * plane, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:
+            chunk = max(1, min(nloc, (2 << 30) // plane))
+            pinned = torch.empty(chunk * plane, dtype=torch.uint8, pin_memory=True)
         x, y, y2 = power.arrays()
         eig_tab = synth.read_eigmodes(P.PLT_filename)[1] if qplt else None
         h2d = x.nbytes * 3 + (eig_tab.nbytes if qplt else 0)
@@ -354,7 +359,7 @@ def main_b200(args, rank, world, local_rank):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": N**3 / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(N**3 * rb), "steps": nsteps, "seconds_per_step": float(dt.item()),
-               "note": "host spline+eigenmode tables -> device, records -> pinned host in 2 GiB chunks, wall clock"}
+               "note": f"host spline+eigenmode tables -> device, every record -> pinned host ({chunk} planes per fetch call), wall clock"}
 
     if rank == 0:
         peak, peak_src = peaks()
