@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     const int tid = threadIdx.x, p = tid % NP, b = tid / NP;
     constexpr int half = N / 2;
     // single GPU: y = 0 .. N/2.  Slab rank: its h primary rows, plus the Nyquist row on rank 0.
-    const int y = (sg.G == 1) ? (int) blockIdx.y : ((int) blockIdx.y < sg.h ? sg.rank * sg.h + (int) blockIdx.y : half);
+    // (in groups: blockIdx.y counts the group's nly rows; one extra block on rank 0's first group is the Nyquist row)
+    const int y = (sg.G == 1) ? (int) blockIdx.y
+                              : ((int) blockIdx.y < sg.nly ? sg.rank * sg.h + sg.ly0 + (int) blockIdx.y : half);
     const int z = blockIdx.x;
     if (y == 0 && z > half) return;  // produced as the twin row of (0, N-z)
 
@@ -211,20 +213,32 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     cplx *S         = reinterpret_cast<cplx *>(smem_raw);
     constexpr int M = N / 16;
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
-    const int rows = sg.na * 2 * sg.h;          // x-rows per z plane of the stage-1 buffer
-    const int row  = blockIdx.y;                // a * 2h + slot
-    const int x    = blockIdx.x * T + p;
+    const int rows = sg.na * 2 * sg.h;  // x-rows per z plane of the stage-1 buffer
     const long long nstride = (long long) rows * N;
-    const long long base    = (long long) row * N + x;
-    cplx v[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
-    const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
     const int np = N / sg.G;
+    // persistent CTAs over the tiles (x tile, array, slot of this group): the pass is NVLink-bound, so
+    // a limited number of CTAs saturates the links and leaves the other SMs to the generation
+    // kernel of the next group, which runs concurrently on another stream
+    constexpr int XT = N / T;
+    const int nsl    = 2 * sg.nly;
+    const long long ntiles = (long long) XT * nsl * sg.na;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int xt = (int) (t % XT);
+        const int rr = (int) (t / XT), sidx = rr % nsl, a = rr / nsl;
+        const int slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
+        const int row  = a * 2 * sg.h + slot;
+        const int x    = xt * T + p;
+        const long long base = (long long) row * N + x;
+        cplx v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const int z = bo + M * e, r = z / np, zl = z % np;
-        st_stream(&peers.recv[r][(((long long) sg.rank * np + zl) * rows + row) * N + x], v[e]);
+        for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
+        const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int z = bo + M * e, r = z / np, zl = z % np;
+            st_stream(&peers.recv[r][(((long long) sg.rank * np + zl) * rows + row) * N + x], v[e]);
+        }
+        __syncthreads();  // the exchange image is reused by the next tile
     }
 }
 
@@ -632,7 +646,7 @@ static int launch_genx_t(const GenParams &g, const SlabGeom &sg, cplx *cube, con
     size_t smem = fft_tile_smem(N, NP) + (size_t) 6 * N * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gen_xfft_kernel<N, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    dim3 grid(N, sg.G == 1 ? N / 2 + 1 : sg.h + (sg.rank == 0 ? 1 : 0), 1);
+    dim3 grid(N, sg.G == 1 ? N / 2 + 1 : sg.nly + ((sg.rank == 0 && sg.ly0 == 0) ? 1 : 0), 1);
     gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, sg, cube, tw);
     return (int) cudaGetLastError();
 }
@@ -674,8 +688,13 @@ static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *p
     if (e != cudaSuccess) return (int) e;
     PeerTable pt;
     for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
-    dim3 grid(N / T, sg.na * 2 * sg.h, 1);
-    fft_tile_p2p_kernel<N, T><<<grid, T *(N / 16), smem, st>>>(b1, sg, pt, tw);
+    const long long ntiles = (long long) (N / T) * 2 * sg.nly * sg.na;
+    long long nctas = persistent_ctas((const void *) fft_tile_p2p_kernel<N, T>, T * (N / 16), smem);
+    // about two thirds of the SMs keep NVLink saturated and leave room for the overlapped generation kernel
+    const int lim = env_int("ZPLT_P2P_CTAS", 96);  // 0: as many as fit
+    if (lim > 0 && lim < nctas) nctas = lim;
+    if (nctas > ntiles) nctas = ntiles;
+    fft_tile_p2p_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw);
     return (int) cudaGetLastError();
 }
 

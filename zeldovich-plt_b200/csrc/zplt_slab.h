@@ -34,6 +34,9 @@ struct SlabGeom {
     int h;     // primary rows per rank = N / (2G)  (a power of two, like N and G)
     int na;    // packed arrays
     int log2h;
+    // stage 1 can run in groups of primary rows [ly0, ly0+nly) (and their partners' slots
+    // h+ly0 ...), so that generating one group overlaps with sending the previous one
+    int ly0, nly;
 };
 
 // which rank owns row y, and in which of its 2h slots
