@@ -1,1 +1,3 @@
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e'])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('qPLT', d['ms_per_step'], d['stage_ms'])"
+python bench.py --za --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ZA', d['ms_per_step'], d['stage_ms'])"

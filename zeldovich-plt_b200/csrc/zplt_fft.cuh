@@ -152,7 +152,19 @@ struct FftSmem {
 // One middle/last pass: radix R, K = product of earlier radices, L = N/(K*R).
 // Reads its inputs from the pencil's shared-memory image S (written by the previous pass),
 // leaves the DFT outputs (twiddled unless LAST) in v[j*R + k] for butterfly j = 0..16/R-1.
-template <int N, int T, int R, int K, bool LAST>
+// W^(base*k), k = 1..R-1: either the multiplication tree or, for kernels that are FP64-bound and have
+// load/store head-room (the contiguous-row generation kernel), R-1 loads from the W_N table.
+template <int R, bool TWLOAD>
+__device__ __forceinline__ void twiddle_set(const cplx *__restrict__ tw, int base, cplx (&pw)[16]) {
+    if constexpr (TWLOAD) {
+#pragma unroll
+        for (int k = 1; k < R; k++) pw[k] = __ldg(&tw[base * k]);
+    } else {
+        twiddle_powers<R>(__ldg(&tw[base]), pw);
+    }
+}
+
+template <int N, int T, int R, int K, bool LAST, bool TWLOAD = false>
 __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cplx *__restrict__ tw) {
     constexpr int M  = N / 16;
     constexpr int L  = N / (K * R);
@@ -172,7 +184,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
             const int q  = b + j * M;
             const int kk = q / L, l = q % L;
             cplx pw[16];
-            twiddle_powers<R>(__ldg(&tw[K * l]), pw);
+            twiddle_set<R, TWLOAD>(tw, K * l, pw);
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 cplx x = v[j * R + k];
@@ -197,7 +209,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[16], cplx *S, int b, const cp
 // exchange and the warps of a CTA drift apart (FP64 and shared-memory phases overlap).
 // WL = false keeps the natural output order (bo == b) at the price of two more CTA barriers: the
 // contiguous-row kernel needs it, because the slot permutation would break its coalesced row stores.
-template <int N, int T, bool WL = true>
+template <int N, int T, bool WL = true, bool TWLOAD = false>
 __device__ __forceinline__ int fft_pencil(cplx (&v)[16], cplx *S, int b, const cplx *__restrict__ tw) {
     typedef FftPlan<N> P;
     typedef FftSmem<N, T> SM;
@@ -207,7 +219,7 @@ __device__ __forceinline__ int fft_pencil(cplx (&v)[16], cplx *S, int b, const c
     if constexpr (P::PASSES > 1) {
         {
             cplx pw[16];
-            twiddle_powers<16>(__ldg(&tw[b]), pw);
+            twiddle_set<16, TWLOAD>(tw, b, pw);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 cplx x = v[k];
@@ -219,7 +231,7 @@ __device__ __forceinline__ int fft_pencil(cplx (&v)[16], cplx *S, int b, const c
         if constexpr (P::PASSES == 2) {
             fft_pass<N, T, P::R2, 16, true>(v, S, b, tw);
         } else if constexpr (!WL) {
-            fft_pass<N, T, P::R2, 16, false>(v, S, b, tw);
+            fft_pass<N, T, P::R2, 16, false, TWLOAD>(v, S, b, tw);
             fft_pass<N, T, P::R3, 16 * P::R2, true>(v, S, b, tw);
         } else {
             constexpr int R3 = P::R3;

@@ -9,6 +9,9 @@
 //                    density_variance and max_disp.
 #include <cstdlib>
 
+#ifndef ZPLT_GENX_TWLOAD
+#define ZPLT_GENX_TWLOAD false  // measured: table-loaded twiddles 35.4 ms vs multiplication tree 34.5 ms
+#endif
 #ifndef ZPLT_LDHINT
 #define ZPLT_LDHINT 1
 #endif
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
             if (origin_row && side == 0 && x == 0) val = make_double2(0.0, 0.0);
             v[e] = val;
         }
-        const int bo = fft_pencil<N, NP, false>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);  // natural order: whole rows are stored
+        const int bo = fft_pencil<N, NP, false, ZPLT_GENX_TWLOAD>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);  // natural order: whole rows are stored
         const bool live = (side == 0) || has_twin;
         long long row;
         if (sg.G == 1) {
