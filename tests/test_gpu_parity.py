@@ -422,3 +422,34 @@ def test_density_planes_qdensity(pkg, oracle):
             d = np.fromfile(os.path.join(tmp, "ic_out", "density32"), dtype=np.float32).reshape(32, 32, 32)
             assert np.array_equal(d, dens)
             assert ("maximum component-wise" in r.stderr) == (qd == 1)
+
+
+def test_full_size_oversampling_property(pkg, oracle):
+    """BASELINE full size on one GPU: PPD=1024 with ZD_k_cutoff=2 sampled at even lattice sites carries exactly the
+    modes of PPD=512 (size-independent property; the oracle is too slow at this size).  Also: ids, zero padding,
+    emission is idempotent (the cube is not modified by zplt_emit_planes)."""
+    import torch
+
+    if torch.cuda.mem_get_info()[0] < (60 << 30):
+        pytest.skip("needs ~40 GB of free device memory")
+    pk = helpers.wmap_pk()
+    big, P, _ = make_ctx(pkg, default_kw(ppd=1024, k_cutoff=2.0), pk, None)
+    big.generate()
+    small, P2, _ = make_ctx(pkg, default_kw(ppd=512), pk, None)
+    small.generate()
+    worst = 0.0
+    for z in (0, 2, 510, 1022):
+        a = big.fetch_planes(z, 1).reshape(1024, 1024)
+        assert np.array_equal(a["ijk"][..., 0], np.full((1024, 1024), z))
+        assert np.array_equal(a["ijk"][..., 1], np.arange(1024)[:, None].repeat(1024, 1))
+        assert np.array_equal(a["ijk"][..., 2], np.arange(1024)[None, :].repeat(1024, 0))
+        assert np.all(a["pad"] == 0)
+        again = big.fetch_planes(z, 1)
+        assert np.array_equal(again.view(np.uint8), a.reshape(-1).view(np.uint8))
+        b = small.fetch_planes(z // 2, 1).reshape(512, 512)
+        sub = a[::2, ::2]
+        for f in ("displ", "vel"):
+            worst = max(worst, float(np.abs(sub[f].astype(np.float64) - b[f].astype(np.float64)).max() / np.abs(b[f]).max()))
+    assert worst < 2e-7, worst
+    big.close()
+    small.close()

@@ -95,6 +95,7 @@ struct zplt_ctx {
     double *eig;
     cplx *tw;
     double *stats;
+    float2 *scratch;  // per-SM parking space of the emission kernel (256 SMs x 16 x 512 float2 = 16 MB)
     bool have_power, have_eig, generated;
     // fetch staging
     unsigned char *stage_dev[2];
@@ -251,6 +252,7 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     CK(cudaMalloc((void **) &c->ptab, c->ptab_count * sizeof(double)));
     g.ptab = c->ptab;
     CK(cudaMalloc((void **) &c->stats, ZPLT_STAT_SLOTS * 8 * sizeof(double)));
+    CK(cudaMalloc((void **) &c->scratch, (size_t) 256 * 16 * 512 * sizeof(float2)));
     CK(cudaMemsetAsync(c->stats, 0, ZPLT_STAT_SLOTS * 8 * sizeof(double), c->stream));
     *out = c;
     return ZPLT_OK;
@@ -273,6 +275,7 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     cudaFree(c->eig);
     cudaFree(c->tw);
     cudaFree(c->stats);
+    cudaFree(c->scratch);
     for (int i = 0; i < 2; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
         cudaEventDestroy(c->stage_free[i]);
@@ -486,6 +489,7 @@ extern "C" int zplt_emit_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, voi
     ep.out          = (unsigned char *) device_out;
     ep.dens         = device_density;
     ep.stats        = c->stats;
+    ep.scratch      = (getenv("ZPLT_EMIT_SCRATCH") && atoi(getenv("ZPLT_EMIT_SCRATCH")) == 0) ? nullptr : c->scratch;
     {
         const char *e = getenv("ZPLT_EMIT_PREFETCH");
         ep.prefetch = e ? atoi(e) : 1;

@@ -46,6 +46,11 @@ __device__ __forceinline__ void st_stream(cplx *p, cplx v) {
 // resident CTAs per SM the register budget is tuned for: 512 threads of 128 registers fill an SM
 constexpr int min_ctas(int threads) { return threads >= 512 ? 1 : (512 / threads > 8 ? 8 : 512 / threads); }
 
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // One CTA per tile by default (x tile fastest, so that CTAs running at the same time cover
@@ -424,6 +429,12 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
+                if (qplt && ep.scratch != nullptr) {
+                    // park (displ0, displ1) in this SM's L2-resident scratch: the record is then written whole, as
+                    // two back-to-back 16-byte stores, when A3 is done — no partially written 32-byte sectors in L2
+                    ep.scratch[((size_t) smid() * 16 + e) * NT + tid] = make_float2((float) v[e].y, (float) v[e].x);
+                    continue;
+                }
                 *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), (float) v[e].y, (float) v[e].x);
                 if (!qplt)
                     *reinterpret_cast<float4 *>(rec + 16) =
@@ -454,9 +465,16 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
     } else {  // A == 3: Re = vel[1] -> vel[1], Im = vel[2] -> vel[0]
         if (ep.out == nullptr) {
         } else if (rvzel) {
+            const unsigned int w1 = (unsigned int) (unsigned short) x;
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
+                const int y = b + M * e;
+                unsigned char *rec = rec0 + (size_t) y * N * rb;
+                if (ep.scratch != nullptr) {
+                    const float2 d01 = ep.scratch[((size_t) smid() * 16 + e) * NT + tid];
+                    const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
+                    *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), d01.x, d01.y);
+                }
                 *reinterpret_cast<float4 *>(rec + 16) =
                    make_float4(keep[(0 * 16 + e) * NT + tid], (float) v[e].y, (float) v[e].x, keep[(1 * 16 + e) * NT + tid]);
             }
@@ -736,12 +754,22 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long
     size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
     dim3 grid(N / T, (unsigned) nz, 1);
     const bool slab = sg.G > 1, rvzel = ep.icformat == 1;
+    EmitParams ep2 = ep;
+    if (ep2.scratch != nullptr) {
+        // the per-SM parking space is only safe when CTAs of this kernel never share an SM, and large enough only up to 512 threads
+        int per_sm = 0;
+        if (rvzel && slab)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, true, true>, T * (N / 16), smem);
+        else if (rvzel)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, false, true>, T * (N / 16), smem);
+        if (per_sm != 1 || T * (N / 16) > 512 || !rvzel || !ep.qPLT) ep2.scratch = nullptr;
+    }
 #define ZPLT_EMIT_LAUNCH(SL, RV)                                                                                              \
     {                                                                                                                         \
         cudaError_t e = cudaFuncSetAttribute(fft_emit_strided_kernel<N, T, SL, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int) smem);                                                                     \
         if (e != cudaSuccess) return (int) e;                                                                                 \
-        fft_emit_strided_kernel<N, T, SL, RV><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep, tw);                    \
+        fft_emit_strided_kernel<N, T, SL, RV><<<grid, T *(N / 16), smem, st>>>(cube, sg, z_first, ep2, tw);                    \
     }
     if (slab && rvzel) ZPLT_EMIT_LAUNCH(true, true)
     else if (slab) ZPLT_EMIT_LAUNCH(true, false)
