@@ -95,7 +95,7 @@ struct zplt_ctx {
     double *eig;
     cplx *tw;
     double *stats;
-    float2 *scratch;  // per-SM parking space of the emission kernel (256 SMs x 16 x 512 float2 = 16 MB)
+    void *scratch;  // per-SM parking space of the emission kernel (256 SMs x 16 x 512 x 24 B = 50 MB)
     bool have_power, have_eig, generated;
     // fetch staging
     unsigned char *stage_dev[2];
@@ -252,7 +252,7 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     CK(cudaMalloc((void **) &c->ptab, c->ptab_count * sizeof(double)));
     g.ptab = c->ptab;
     CK(cudaMalloc((void **) &c->stats, ZPLT_STAT_SLOTS * 8 * sizeof(double)));
-    CK(cudaMalloc((void **) &c->scratch, (size_t) 256 * 16 * 512 * sizeof(float2)));
+    CK(cudaMalloc((void **) &c->scratch, (size_t) 256 * 16 * 512 * 24));
     CK(cudaMemsetAsync(c->stats, 0, ZPLT_STAT_SLOTS * 8 * sizeof(double), c->stream));
     *out = c;
     return ZPLT_OK;

@@ -432,7 +432,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
                 if (qplt && ep.scratch != nullptr) {
                     // park (displ0, displ1) in this SM's L2-resident scratch: the record is then written whole, as
                     // two back-to-back 16-byte stores, when A3 is done — no partially written 32-byte sectors in L2
-                    ep.scratch[((size_t) smid() * 16 + e) * NT + tid] = make_float2((float) v[e].y, (float) v[e].x);
+                    reinterpret_cast<float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid] = make_float2((float) v[e].y, (float) v[e].x);
                     continue;
                 }
                 *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), (float) v[e].y, (float) v[e].x);
@@ -444,11 +444,19 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
         } else {
             // ids and the whole displacement (and, without qPLT, the whole velocity) in one burst of
             // back-to-back stores to consecutive bytes, so that L2 sees complete sectors
+            double *sd = reinterpret_cast<double *>(ep.scratch);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 const double pos0 = keepd[e * NT + tid];
+                if (qplt && sd != nullptr) {
+                    // qPLT (RVdoubleZel): park the displacement in this SM's L2-resident scratch, the whole
+                    // 56-byte record is written in one burst when A3 is done
+                    double *q = sd + (((size_t) smid() * 16 + e) * NT + tid) * 3;
+                    q[0] = v[e].y, q[1] = v[e].x, q[2] = pos0;
+                    continue;
+                }
                 if (L.off_ijk >= 0)
                     *reinterpret_cast<ushort4 *>(rec + L.off_ijk) =
                        make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
@@ -471,7 +479,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 if (ep.scratch != nullptr) {
-                    const float2 d01 = ep.scratch[((size_t) smid() * 16 + e) * NT + tid];
+                    const float2 d01 = reinterpret_cast<const float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid];
                     const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
                     *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), d01.x, d01.y);
                 }
@@ -479,9 +487,20 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
                    make_float4(keep[(0 * 16 + e) * NT + tid], (float) v[e].y, (float) v[e].x, keep[(1 * 16 + e) * NT + tid]);
             }
         } else {
+            const double *sd = reinterpret_cast<const double *>(ep.scratch);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                unsigned char *rec = rec0 + (size_t) (b + M * e) * N * rb;
+                const int y = b + M * e;
+                unsigned char *rec = rec0 + (size_t) y * N * rb;
+                if (sd != nullptr) {
+                    const double *q = sd + (((size_t) smid() * 16 + e) * NT + tid) * 3;
+                    if (L.off_ijk >= 0)
+                        *reinterpret_cast<ushort4 *>(rec + L.off_ijk) =
+                           make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
+                    put(rec, L.off_d[0], q[0], dbl);
+                    put(rec, L.off_d[1], q[1], dbl);
+                    put(rec, L.off_d[2], q[2], dbl);
+                }
                 put(rec, L.off_v[0], v[e].y, dbl);
                 put(rec, L.off_v[1], v[e].x, dbl);
                 put(rec, L.off_v[2], keepd[e * NT + tid], dbl);
@@ -762,7 +781,11 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, true, true>, T * (N / 16), smem);
         else if (rvzel)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, false, true>, T * (N / 16), smem);
-        if (per_sm != 1 || T * (N / 16) > 512 || !rvzel || !ep.qPLT) ep2.scratch = nullptr;
+        else if (slab)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, true, false>, T * (N / 16), smem);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, false, false>, T * (N / 16), smem);
+        if (per_sm != 1 || T * (N / 16) > 512 || !ep.qPLT) ep2.scratch = nullptr;
     }
 #define ZPLT_EMIT_LAUNCH(SL, RV)                                                                                              \
     {                                                                                                                         \

@@ -32,7 +32,7 @@ struct EmitParams {
     float *dens;        // optional density planes, float32, (z - z0, y, x) order (ZD_qdensity); NULL: none
     double *stats;      // [ZPLT_STAT_SLOTS][8]: sum dens^2, +max[3], -max[3], pad
     int prefetch;       // L2-prefetch the next packed array of the tile during the transform
-    float2 *scratch;    // per-SM, L2-resident parking space [sm][16][threads] (RVZel + qPLT, one CTA per SM), or NULL
+    void *scratch;      // per-SM, L2-resident parking space [sm][16][threads] x 24 B (qPLT, one CTA per SM), or NULL
 };
 #define ZPLT_STAT_SLOTS 64
 
