@@ -213,7 +213,7 @@ def main_reference(args, rank, world):
         last = s
         if sum(times) > 150:  # bounded: keep the whole arm within a few minutes
             break
-    t = max(times) if False else sum(times) / len(times)
+    t = sum(times) / len(times)
     val = ppd**3 / t
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
@@ -408,10 +408,7 @@ def main_b200(args, rank, world, local_rank):
                 "nvlink_gbs_per_gpu": 16 * na * N**3 / world * (world - 1) / world
                 / (((stage[0] + stage[1]) if args.exchange == "p2p" else a2a_ms) * 1e-3) / 1e9,
                 "reference_peer_copy_gbs": 770.0},
-            "stats": {"rms_density": (stats["density_variance"] / args.steps / max(args.warmup + 1, 1) / N**3) ** 0.5
-                      if False else None},
         }
-        line.pop("stats")
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

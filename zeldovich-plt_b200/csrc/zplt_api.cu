@@ -129,9 +129,22 @@ static int upload(void **dptr, const void *h, size_t bytes, cudaStream_t st) {
     return 0;
 }
 
+static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partial);
+
 extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     if (!cfg || !out) return fail(ZPLT_EINVAL, "null argument");
-    *out = nullptr;
+    *out             = nullptr;
+    zplt_ctx *partial = nullptr;
+    int rc            = create_impl(cfg, out, &partial);
+    if (rc != ZPLT_OK && partial) {  // release whatever had been set up before the failure
+        std::string keep = g_err;
+        zplt_destroy(partial);
+        g_err = keep;
+    }
+    return rc;
+}
+
+static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partial) {
     const long long N = cfg->ppd;
     if (N < 16 || N > 2048 || (N & (N - 1)))
         return fail(ZPLT_EINVAL, "ppd=%lld unsupported: this build handles power-of-two ppd in [16, 2048]", N);
@@ -158,6 +171,7 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     if (const char *e = getenv("ZPLT_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) atoi(e));
     zplt_ctx *c = new zplt_ctx();
     memset(c, 0, sizeof(*c));
+    *partial  = c;
     c->cfg    = *cfg;
     c->N      = (int) N;
     c->na     = cfg->qPLT ? 4 : 2;
@@ -254,14 +268,15 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
     CK(cudaMalloc((void **) &c->stats, ZPLT_STAT_SLOTS * 8 * sizeof(double)));
     CK(cudaMalloc((void **) &c->scratch, (size_t) 256 * 16 * 512 * 24));
     CK(cudaMemsetAsync(c->stats, 0, ZPLT_STAT_SLOTS * 8 * sizeof(double), c->stream));
-    *out = c;
+    *out     = c;
+    *partial = nullptr;
     return ZPLT_OK;
 }
 
 extern "C" void zplt_destroy(zplt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (int r = 0; r < 16; r++)
         if (c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->own_cube && c->cube) cudaFree(c->cube);
@@ -278,16 +293,19 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     cudaFree(c->scratch);
     for (int i = 0; i < 2; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
-        cudaEventDestroy(c->stage_free[i]);
-        cudaEventDestroy(c->stage_full[i]);
+        if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
+        if (c->stage_full[i]) cudaEventDestroy(c->stage_full[i]);
     }
-    for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev_gen[i]);
-    for (int i = 0; i < 2 * ZPLT_MAX_EMIT_EVENTS; i++) cudaEventDestroy(c->ev_emit[i]);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->xchg_stream);
-    for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev_group[i]);
-    cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < 4; i++)
+        if (c->ev_gen[i]) cudaEventDestroy(c->ev_gen[i]);
+    for (int i = 0; i < 2 * ZPLT_MAX_EMIT_EVENTS; i++)
+        if (c->ev_emit[i]) cudaEventDestroy(c->ev_emit[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
+    for (int i = 0; i < 16; i++)
+        if (c->ev_group[i]) cudaEventDestroy(c->ev_group[i]);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
 }
 

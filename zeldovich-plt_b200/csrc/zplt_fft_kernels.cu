@@ -286,49 +286,6 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Which record field each lane fills.  Array a of the packed set carries
-// (reference src/output.cpp:95-108): A0 = dens + i pos[0], A1 = pos[1] + i pos[2],
-// A2 = . + i vel[0], A3 = vel[1] + i vel[2]; records store displ = (pos[2], pos[1], pos[0])
-// and vel = (vel[2], vel[1], vel[0]) (reference src/output.cpp:128-155).  Without qPLT the
-// velocity is pos * vnorm, written by the lane that owns that pos component.
-struct LaneFields {
-    int o_re, o_im;    // record offsets for Re / Im of this lane's array (-1: not stored)
-    int o_vre, o_vim;  // offsets for Re*vnorm / Im*vnorm (ZA velocities)
-    int o_ijk;         // lane 0 also writes the particle id
-    int s_re, s_im;    // statistics slot (0..2 = pos component) of Re / Im, -1: none
-};
-__device__ __forceinline__ LaneFields lane_fields(int a, const RecLayout &L, int qPLT) {
-    LaneFields f = {-1, -1, -1, -1, -1, -1, -1};
-    if (a == 0) {
-        f.o_ijk = L.off_ijk;
-        f.o_im  = L.off_d[2];
-        f.s_im  = 0;
-        if (!qPLT) f.o_vim = L.off_v[2];
-    } else if (a == 1) {
-        f.o_re = L.off_d[1];
-        f.o_im = L.off_d[0];
-        f.s_re = 1;
-        f.s_im = 2;
-        if (!qPLT) f.o_vre = L.off_v[1], f.o_vim = L.off_v[0];
-    } else if (a == 2) {
-        f.o_im = L.off_v[2];
-    } else {
-        f.o_re = L.off_v[1];
-        f.o_im = L.off_v[0];
-    }
-    return f;
-}
-
-// ------------------------------------------------------------------ y FFT + emission
-// Last axis (y, stride N) fused with particle emission (reference WriteParticlesSlab,
-// src/output.cpp:41-234).  A CTA owns the tile (z, all y, T consecutive x) and walks the
-// packed arrays one after the other — the array index is uniform across the CTA, so the
-// per-array record logic has no divergence.  Nothing is written back to the cube: the
-// transformed values go straight from registers into the records.
-//   RVZel (the headline format): the 32-byte record is written as two aligned 16-byte
-//   halves, [i j k pad | displ0 displ1] from A1 alone and [displ2 | vel0 vel1 vel2] from
-//   A0/A3/A2, with the two floats that must wait (Im A0, Im A2) parked in shared memory.
-//   Other formats: each field is stored as soon as its array has been transformed.
 // Reduce three per-thread partials over the warp and leave them in s_red[warp][slot]
 // (slot 0 is a sum, every other slot a maximum; slot 7 is scratch).
 template <int NT>
@@ -566,67 +523,6 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     }
 }
 
-// Record emission from the fully transformed cube (reference WriteParticlesSlab,
-// src/output.cpp:41-234): one thread per particle, records staged in shared memory and
-// copied out with 128-bit stores.
-__global__ void __launch_bounds__(256) emit_kernel(const cplx *__restrict__ cube, int N, long long z_first, EmitParams ep) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_red[8][8];
-    const int tid = threadIdx.x;
-    const long long z = z_first + blockIdx.y;
-    const long long i0 = (long long) blockIdx.x * 256;  // first particle of this block within the plane
-    const long long i  = i0 + tid;                      // y*N + x
-    const int y = (int) (i / N), x = (int) (i % N);
-    const long long N3 = (long long) N * N * N;
-    const long long idx = z * N * (long long) N + i;
-    const RecLayout L = rec_layout(ep.icformat);
-    const int rb = ep.record_bytes, dbl = L.dbl;
-    unsigned char *rec = smem_raw + (size_t) tid * rb;
-    const cplx a0 = ld_stream(&cube[idx]), a1 = ld_stream(&cube[N3 + idx]);
-    const double dens = a0.x;
-    const double pos0 = a0.y, pos1 = a1.x, pos2 = a1.y;
-    double vel0, vel1, vel2;
-    if (ep.qPLT) {
-        const cplx a2 = ld_stream(&cube[2 * N3 + idx]), a3 = ld_stream(&cube[3 * N3 + idx]);
-        vel0 = a2.y, vel1 = a3.x, vel2 = a3.y;
-    } else {
-        vel0 = pos0 * ep.vnorm, vel1 = pos1 * ep.vnorm, vel2 = pos2 * ep.vnorm;
-    }
-    if (L.off_ijk >= 0)
-        *reinterpret_cast<ushort4 *>(rec + L.off_ijk) = make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
-    put(rec, L.off_d[0], pos2, dbl);
-    put(rec, L.off_d[1], pos1, dbl);
-    put(rec, L.off_d[2], pos0, dbl);
-    put(rec, L.off_v[0], vel2, dbl);
-    put(rec, L.off_v[1], vel1, dbl);
-    put(rec, L.off_v[2], vel0, dbl);
-    double q[7] = {dens * dens, fmax(pos0, 0.0), fmax(pos1, 0.0), fmax(pos2, 0.0), fmax(-pos0, 0.0), fmax(-pos1, 0.0), fmax(-pos2, 0.0)};
-    q[0] = warp_sum(q[0]);
-#pragma unroll
-    for (int k = 1; k < 7; k++) q[k] = warp_max(q[k]);
-    if ((tid & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < 7; k++) s_red[tid >> 5][k] = q[k];
-    }
-    __syncthreads();
-    {
-        const size_t bytes = (size_t) 256 * rb;
-        unsigned char *dst = ep.out + ((size_t) ((z - ep.z0) * N * (long long) N + i0)) * rb;
-        const int4 *s4 = reinterpret_cast<const int4 *>(smem_raw);
-        int4 *d4       = reinterpret_cast<int4 *>(dst);
-        for (size_t k = tid; k < bytes / 16; k += 256) __stcs(&d4[k], s4[k]);
-    }
-    if (tid < 7) {
-        double acc = s_red[0][tid];
-        for (int w = 1; w < 8; w++) acc = (tid == 0) ? acc + s_red[w][tid] : fmax(acc, s_red[w][tid]);
-        double *slot = ep.stats + 8 * ((blockIdx.x + blockIdx.y * gridDim.x) % ZPLT_STAT_SLOTS);
-        if (tid == 0)
-            atomicAdd(&slot[0], acc);
-        else
-            atomicMax(reinterpret_cast<unsigned long long *>(&slot[tid]), (unsigned long long) __double_as_longlong(acc));
-    }
-}
-
 // ------------------------------------------------------------------ dispatch -------
 static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
@@ -815,14 +711,6 @@ int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, 
     ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, sg, z_first, nz, ep, tw, st, launches)
     ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, sg, z_first, nz, ep, tw, st, launches)
     return (int) cudaErrorInvalidValue;
-}
-
-int launch_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st, int *launches) {
-    if (((long long) N * N) % 256) return (int) cudaErrorInvalidValue;
-    dim3 grid((unsigned) ((long long) N * N / 256), (unsigned) nz, 1);
-    emit_kernel<<<grid, 256, 256 * ep.record_bytes, st>>>(cube, N, z_first, ep);
-    if (launches) *launches += 1;
-    return (int) cudaGetLastError();
 }
 
 }  // namespace zplt

@@ -50,8 +50,6 @@ int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx 
 // y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
                             const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches);
-// Record emission for planes [z_first, z_first+nz) of a fully transformed [na][N][N][N] cube.
-int launch_emit(int N, const cplx *cube, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st, int *launches);
 
 int launch_power_table(double *ptab, long long count, double fundamental2, int is_powerlaw, double index, int n,
                        const double *x, const double *y, const double *y2, double normalization, double smooth2,
