@@ -266,7 +266,7 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     CK(cudaMalloc((void **) &c->ptab, c->ptab_count * sizeof(double)));
     g.ptab = c->ptab;
     CK(cudaMalloc((void **) &c->stats, ZPLT_STAT_SLOTS * 8 * sizeof(double)));
-    CK(cudaMalloc((void **) &c->scratch, (size_t) 256 * 16 * 512 * 24));
+    CK(cudaMalloc((void **) &c->scratch, ZPLT_SCRATCH_BYTES));
     CK(cudaMemsetAsync(c->stats, 0, ZPLT_STAT_SLOTS * 8 * sizeof(double), c->stream));
     *out     = c;
     *partial = nullptr;

@@ -233,6 +233,158 @@ __device__ __forceinline__ void primary_mode(const GenParams &g, int x, int y, i
     m.f  = f;
 }
 
+// ------------------------------------------------------------------ runs of modes ----
+// The fused generation kernel draws RUN consecutive x of one row (y, z) per thread.  Everything
+// that depends on (y, z) only is formed once per thread (RowConst); consecutive kx are consecutive
+// positions of the generator, so one jump serves the whole run; and when the RUN
+// sites fall into one cell of the eigenmode table (always, for ppd >= RUN * ppd_e, except next to the
+// table's Nyquist gap) the eight corners are loaded once and reduced along y and z before the
+// per-site x interpolation.  The RUN sites are independent straight-line code: the instruction-level
+// parallelism hides the FP64 latency that one mode per thread exposes.
+__device__ __forceinline__ void eig_axis(const GenParams &g, int ik, int &lo, int &hi, double &fr) {
+    const int half = g.pe / 2;
+    double f = g.eig_scale * ik;
+    if (f > half && f < half + 1) f = floor(f + 1);  // never interpolate across the Nyquist gap
+    lo = (int) f;
+    hi = lo + 1;
+    if (hi == g.pe) hi = 0;
+    fr = f - lo;
+}
+
+struct RowConst {
+    int ky, kz, n2yz;
+    u128 s_yz;                    // generator state of the row before the jump along x
+    int ylo, yhi, zlo, zhi;       // eigenmode cell along y and z (interpolated tables only)
+    double wyz[4];                // bilinear weights (ylo,zlo) (ylo,zhi) (yhi,zlo) (yhi,zhi)
+};
+
+__device__ __forceinline__ RowConst row_const(const GenParams &g, int y, int z) {
+    RowConst rc;
+    rc.ky   = y;
+    rc.kz   = wrap_k(z, g.N, g.half);
+    rc.n2yz = rc.ky * rc.ky + rc.kz * rc.kz;
+    rc.s_yz = apply(g.zjump[z], g.ystate[y]);
+    rc.ylo = rc.yhi = rc.zlo = rc.zhi = 0;
+    rc.wyz[0] = rc.wyz[1] = rc.wyz[2] = rc.wyz[3] = 0.0;
+    if (g.qPLT && !g.eig_direct) {
+        double fy, fz;
+        eig_axis(g, y, rc.ylo, rc.yhi, fy);
+        eig_axis(g, rc.kz < 0 ? -rc.kz : rc.kz, rc.zlo, rc.zhi, fz);  // stored half-space is +kz
+        if (rc.zhi > g.pe / 2) rc.zhi = g.pe / 2;                       // weight-0 corner, see interp_eig
+        rc.wyz[0] = (1 - fy) * (1 - fz);
+        rc.wyz[1] = (1 - fy) * fz;
+        rc.wyz[2] = fy * (1 - fz);
+        rc.wyz[3] = fy * fz;
+    }
+    return rc;
+}
+
+template <int RUN>
+__device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &rc, int x0, double (&Dr)[RUN], double (&Di)[RUN],
+                                            double (&s0)[RUN], double (&s1)[RUN], double (&s2)[RUN], double (&ff)[RUN]) {
+    const int N = g.N, half = g.half, ky = rc.ky, kz = rc.kz;
+    int kx[RUN], n2[RUN];
+    bool act[RUN], any = false;
+#pragma unroll
+    for (int j = 0; j < RUN; j++) {
+        kx[j]  = wrap_k(x0 + j, N, half);
+        n2[j]  = kx[j] * kx[j] + rc.n2yz;
+        act[j] = !mode_masked(g, kx[j], ky, kz, n2[j]);
+        any |= act[j];
+        Dr[j] = Di[j] = s0[j] = s1[j] = s2[j] = ff[j] = 0.0;
+    }
+    if (!any) return;
+    // the draws: masked sites consume theirs too, so the run is one walk of the generator.  The only
+    // break is between x = N/2 (kx = +N/2) and x = N/2+1 (kx = -N/2+1); runs are aligned, so it can
+    // only sit between the first and the second site of a run.
+    double u1[RUN], u2[RUN];
+    {
+        u128 s = apply(g.xjump[x0], rc.s_yz);
+#pragma unroll
+        for (int j = 0; j < RUN; j++) {
+            if (j == 1 && x0 == half) s = apply(g.xjump[x0 + 1], rc.s_yz);
+            u1[j] = u64_to_unit(pcg_next(s));
+            u2[j] = u64_to_unit(pcg_next(s));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RUN; j++) box_muller(g, __ldg(&g.ptab[n2[j]]), u1[j], u2[j], Dr[j], Di[j]);
+
+    if (!g.qPLT) {
+#pragma unroll
+        for (int j = 0; j < RUN; j++) {
+            const double q = (n2[j] == 0) ? 0.0 : 1.0 / ((double) n2[j] * g.fundamental);
+            s0[j] = kx[j] * q, s1[j] = ky * q, s2[j] = kz * q, ff[j] = 1.0;
+        }
+    } else {
+        double eh[RUN][4];
+        const int pe = g.pe, hp1 = pe / 2 + 1;
+        const double2 *tab2 = reinterpret_cast<const double2 *>(g.eig);
+        auto ld4 = [tab2](size_t i) {
+            double2 lo = __ldg(&tab2[2 * i]), hi = __ldg(&tab2[2 * i + 1]);
+            return make_double4(lo.x, lo.y, hi.x, hi.y);
+        };
+        const int ikz = kz < 0 ? -kz : kz;
+        if (g.eig_direct) {
+            const int q = pe / N;
+#pragma unroll
+            for (int j = 0; j < RUN; j++) {
+                double4 v = ld4(((size_t) ((x0 + j) * q) * pe + (size_t) (ky * q)) * hp1 + (size_t) (ikz * q));
+                eh[j][0] = v.x, eh[j][1] = v.y, eh[j][2] = v.z, eh[j][3] = v.w;
+            }
+        } else {
+            int xlo[RUN], xhi[RUN];
+            double fx[RUN];
+            bool same = true;
+#pragma unroll
+            for (int j = 0; j < RUN; j++) {
+                eig_axis(g, x0 + j, xlo[j], xhi[j], fx[j]);
+                same = same && (xlo[j] == xlo[0]);
+            }
+            if (same) {
+                // one cell: reduce the corners along y and z once, interpolate along x per site
+                double4 elo = make_double4(0, 0, 0, 0), ehi = make_double4(0, 0, 0, 0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int cy = (c & 2) ? rc.yhi : rc.ylo, cz = (c & 1) ? rc.zhi : rc.zlo;
+                    const double4 a = ld4(((size_t) xlo[0] * pe + (size_t) cy) * hp1 + (size_t) cz);
+                    const double4 b = ld4(((size_t) xhi[0] * pe + (size_t) cy) * hp1 + (size_t) cz);
+                    const double w  = rc.wyz[c];
+                    elo.x = fma(w, a.x, elo.x), elo.y = fma(w, a.y, elo.y), elo.z = fma(w, a.z, elo.z), elo.w = fma(w, a.w, elo.w);
+                    ehi.x = fma(w, b.x, ehi.x), ehi.y = fma(w, b.y, ehi.y), ehi.z = fma(w, b.z, ehi.z), ehi.w = fma(w, b.w, ehi.w);
+                }
+#pragma unroll
+                for (int j = 0; j < RUN; j++) {
+                    const double wl = 1 - fx[j], wh = fx[j];
+                    eh[j][0] = fma(wh, ehi.x, wl * elo.x);
+                    eh[j][1] = fma(wh, ehi.y, wl * elo.y);
+                    eh[j][2] = fma(wh, ehi.z, wl * elo.z);
+                    eh[j][3] = fma(wh, ehi.w, wl * elo.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < RUN; j++) interp_eig(g, x0 + j, ky, ikz, eh[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RUN; j++) {
+            if (kz < 0) eh[j][2] = -eh[j][2];
+            const double dot = kx[j] * eh[j][0] + ky * eh[j][1] + kz * eh[j][2];
+            double q = 1.0 / (dot * g.fundamental);
+            if (n2[j] == 0 || !isfinite(q)) q = 0.0;
+            const double f = (sqrt(1. + 24 * eh[j][3] * g.f_cluster) - 1) * .25;
+            const double rescale = g.qPLTrescale ? exp(g.log_growth_ratio * (g.target_f - f)) : 1.0;
+            q *= rescale;
+            s0[j] = eh[j][0] * q, s1[j] = eh[j][1] * q, s2[j] = eh[j][2] * q, ff[j] = f;
+        }
+    }
+    // masked sites, and the reference's "D != 0." guard (src/zeldovich.cpp:403): everything is zero
+#pragma unroll
+    for (int j = 0; j < RUN; j++) {
+        if (!act[j] || (Dr[j] == 0.0 && Di[j] == 0.0)) Dr[j] = Di[j] = s0[j] = s1[j] = s2[j] = ff[j] = 0.0;
+    }
+}
+
 // Packed entries A0..A3 for the primary site and for its conjugate-structured twin
 // (reference src/zeldovich.cpp:447-466).
 __device__ __forceinline__ void pack_primary(const Mode &m, cplx a[4]) {

@@ -8,6 +8,7 @@
 //                    into displacement/velocity, cast to the ICFormat record, accumulate
 //                    density_variance and max_disp.
 #include <cstdlib>
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #ifndef ZPLT_GENX_TWLOAD
 #define ZPLT_GENX_TWLOAD false  // measured: table-loaded twiddles 35.4 ms vs multiplication tree 34.5 ms
@@ -100,6 +101,107 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_k
     }
 }
 
+// ------------------------------------------------------------------ ring-prefetched strided pass
+// Same transform as fft_tile_kernel, organised so that the SM always has loads in flight: the register
+// file holds exactly one tile (512 threads x 16 complex) and shared memory holds its exchange image, so a
+// second resident tile is impossible — but the 96 KB of shared memory next to the exchange image can
+// receive KP of the next tile's 16 slices (slice e = rows b + M*e, one 128-byte run per row) while the
+// current tile is transformed and stored.  The copies are cp.async.bulk (the TMA unit's 1-D form, one
+// per row, completion counted in bytes on an mbarrier), so they cost no registers and no LSU issue
+// slots; the remaining 16 - KP slices are ordinary loads at the top of the iteration.  CTAs are
+// persistent and take tiles from a device counter (the hardware scheduler's balance, kept).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+       "{\n"
+       ".reg .pred P1;\n"
+       "ZPLT_WAIT:\n"
+       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+       "@P1 bra ZPLT_DONE;\n"
+       "bra ZPLT_WAIT;\n"
+       "ZPLT_DONE:\n"
+       "}" ::"r"(smem_u32(bar)),
+       "r"(parity)
+       : "memory");
+}
+// one slice of a tile: box (2T doubles along x, 1 row, M points along the transform axis, 1 array)
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+       : "memory");
+}
+
+template <int N, int T>
+struct RingSmem {
+    static constexpr size_t EXCHANGE = ((size_t) T * FftSmem<N, T>::PSTRIDE * sizeof(cplx) + 127) / 128 * 128;
+};
+
+template <int N, int T, int KP>
+__global__ void __launch_bounds__(T *(N / 16), 1)
+   fft_tile_ring_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw, unsigned int *__restrict__ counter,
+                        const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem_ring[];
+    constexpr int M  = N / 16;
+    constexpr int NT = T * M;
+    static_assert(KP >= 1 && KP <= 16, "slices");
+    cplx *S            = reinterpret_cast<cplx *>(smem_ring);
+    cplx *L            = reinterpret_cast<cplx *>(smem_ring + RingSmem<N, T>::EXCHANGE);  // [KP][M][T]
+    uint64_t *mbar     = reinterpret_cast<uint64_t *>(smem_ring + RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx));
+    unsigned int *s_nn = reinterpret_cast<unsigned int *>(mbar + 1);
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    const unsigned int ntiles = (unsigned int) (g.grid_x * g.grid_y * g.grid_z);
+    auto tile_base = [&](unsigned int t) {
+        const long long tx = t % g.grid_x, ty = (t / g.grid_x) % g.grid_y, tz = t / ((unsigned int) g.grid_x * g.grid_y);
+        return tz * g.astride + ty * g.ostride + tx * g.tstride;
+    };
+    auto issue_ring = [&](unsigned int t) {
+        if (tid == 0) {
+            mbar_expect_tx(mbar, (unsigned) (KP * M * T * sizeof(cplx)));
+            const int tx = t % g.grid_x, ty = (t / g.grid_x) % g.grid_y, tz = t / ((unsigned int) g.grid_x * g.grid_y);
+#pragma unroll
+            for (int e = 0; e < KP; e++) tma_load_4d(L + (size_t) e * M * T, &tmap, tx * 2 * T, ty, M * e, tz, mbar);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        s_nn[0] = atomicAdd(counter, 1u);
+        s_nn[1] = atomicAdd(counter, 1u);
+    }
+    __syncthreads();
+    unsigned int cur = s_nn[0], nxt = s_nn[1];
+    __syncthreads();
+    if (cur < ntiles) issue_ring(cur);
+    unsigned int parity = 0;
+    while (cur < ntiles) {
+        if (tid == 0) s_nn[0] = atomicAdd(counter, 1u);  // the tile after next
+        const long long base = tile_base(cur) + p;
+        cplx v[16];
+#pragma unroll
+        for (int e = KP; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int e = 0; e < KP; e++) v[e] = L[(size_t) (e * M + b) * T + p];
+        __syncthreads();  // the ring has been read and the exchange image of the previous tile is no longer in use
+        const unsigned int nn = s_nn[0];
+        if (nxt < ntiles) issue_ring(nxt);
+        const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
+#pragma unroll
+        for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (bo + M * e) * g.nstride], v[e]);
+        cur = nxt;
+        nxt = nn;
+    }
+}
+
 // ------------------------------------------------------------------ generation + x FFT
 // Fused mode generation and x-axis FFT (the first of the three axes; the transform is
 // separable so the axis order is free).  One CTA owns R row pairs: row (y, z) of primary
@@ -130,24 +232,62 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     const int z = blockIdx.x;
     if (y == 0 && z > half) return;  // produced as the twin row of (0, N-z)
 
-    // ---- phase 1: draw the primary modes of row (y, z) once ----
-    for (int x = tid; x < N; x += NT) {
-        Mode m;
-        m.Dr = m.Di = m.s0 = m.s1 = m.s2 = m.f = 0.0;
-        if (y < half) primary_mode(g, x, y, z, m);
-        state[0 * N + x] = m.Dr;
-        state[1 * N + x] = m.Di;
-        state[2 * N + x] = m.s0;
-        state[3 * N + x] = m.s1;
-        state[4 * N + x] = m.s2;
-        state[5 * N + x] = m.f;
+    const bool origin_row = (y == 0 && z == 0);
+    const bool has_twin   = (y > 0 && y < half) || (y == 0 && z > 0 && z < half);
+    const int zh = (N - z) % N, yh = (N - y) % N;
+    auto row_of = [&](int a, int side) -> long long {
+        if (sg.G == 1)
+            return (side == 0) ? ((long long) a * N + z) * N * (long long) N + (long long) y * N
+                               : ((long long) a * N + zh) * N * (long long) N + (long long) yh * N;
+        const int ly = (y == half) ? sg.h : y - sg.rank * sg.h;  // slot of the primary row
+        return (side == 0) ? slab_b1_row(sg, a, z, ly) : slab_b1_row(sg, a, zh, (y == 0) ? 0 : sg.h + ly);
+    };
+    constexpr int RUN = N / NT;  // = 16 / NP
+    static_assert(RUN * NT == N && (RUN == 2 || RUN == 4 || RUN == 8), "whole runs");
+
+    // ---- rows without a single unmasked mode (outside the k_cutoff sphere: 1 - pi/4 of all rows; the Nyquist
+    //      row) are zero in every packed array, and so are their transforms: store zeros, skip everything else ----
+    {
+        bool any = false;
+        if (y < half) {
+            const int kz = wrap_k(z, N, half);
+#pragma unroll
+            for (int j = 0; j < RUN; j++) {
+                const int kx = wrap_k(tid * RUN + j, N, half);
+                any |= !mode_masked(g, kx, y, kz, kx * kx + y * y + kz * kz);
+            }
+        }
+        if (!__syncthreads_or(any)) {
+            for (int P = 0; P < 2 * na; P++) {
+                const int a = P % na, side = P / na;
+                if (side == 1 && !has_twin) continue;
+                const long long row = row_of(a, side);
+                for (int i = tid; i < N; i += NT) st_stream(&cube[row + i], make_double2(0.0, 0.0));
+            }
+            return;
+        }
+    }
+
+    // ---- phase 1: draw the primary modes of row (y, z) once, RUN consecutive x per thread ----
+    {
+        double q[6][RUN];
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+#pragma unroll
+            for (int j = 0; j < RUN; j++) q[c][j] = 0.0;
+        if (y < half) {
+            const RowConst rc = row_const(g, y, z);
+            primary_run<RUN>(g, rc, tid * RUN, q[0], q[1], q[2], q[3], q[4], q[5]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+#pragma unroll
+            for (int j = 0; j < RUN; j += 2)
+                *reinterpret_cast<double2 *>(&state[c * N + tid * RUN + j]) = make_double2(q[c][j], q[c][j + 1]);
     }
     __syncthreads();
 
     // ---- phase 2: the 2*na pencils (na arrays x {row, twin row}), NP at a time ----
-    const bool origin_row = (y == 0 && z == 0);
-    const bool has_twin   = (y > 0 && y < half) || (y == 0 && z > 0 && z < half);
-    const int zh = (N - z) % N, yh = (N - y) % N;
     const int rounds = 2 * na / NP;
     for (int rnd = 0; rnd < rounds; rnd++) {
         const int P = rnd * NP + p, a = P % na, side = P / na;
@@ -189,15 +329,8 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
             v[e] = val;
         }
         const int bo = fft_pencil<N, NP, false, ZPLT_GENX_TWLOAD>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);  // natural order: whole rows are stored
-        const bool live = (side == 0) || has_twin;
-        long long row;
-        if (sg.G == 1) {
-            row = (side == 0) ? ((long long) a * N + z) * N * (long long) N + (long long) y * N
-                              : ((long long) a * N + zh) * N * (long long) N + (long long) yh * N;
-        } else {
-            const int ly = (y == half) ? sg.h : y - sg.rank * sg.h;  // slot of the primary row
-            row = (side == 0) ? slab_b1_row(sg, a, z, ly) : slab_b1_row(sg, a, zh, (y == 0) ? 0 : sg.h + ly);
-        }
+        const bool live     = (side == 0) || has_twin;
+        const long long row = row_of(a, side);
         if (live) {
 #pragma unroll
             for (int e = 0; e < 16; e++) st_stream(&cube[row + bo + M * e], v[e]);
@@ -288,13 +421,22 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // Reduce three per-thread partials over the warp and leave them in s_red[warp][slot]
 // (slot 0 is a sum, every other slot a maximum; slot 7 is scratch).
-template <int NT>
+// ACC: the CTA walks several tiles (persistent kernel) and accumulates into s_red, which it zeroed at the start.
+template <int NT, bool ACC = false>
 __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q0, int s0, double q1, int s1, double q2, int s2) {
     if constexpr (NT >= 32) {
         q0 = (s0 == 0) ? warp_sum(q0) : warp_max(q0);
         q1 = warp_max(q1);
         q2 = warp_max(q2);
-        if ((tid & 31) == 0) s_red[tid >> 5][s0] = q0, s_red[tid >> 5][s1] = q1, s_red[tid >> 5][s2] = q2;
+        if ((tid & 31) == 0) {
+            double *r = s_red[tid >> 5];
+            if constexpr (ACC) {
+                r[s0] = (s0 == 0) ? r[s0] + q0 : fmax(r[s0], q0);
+                r[s1] = fmax(r[s1], q1), r[s2] = fmax(r[s2], q2);
+            } else {
+                r[s0] = q0, r[s1] = q1, r[s2] = q2;
+            }
+        }
     } else {
         s_red[tid][s0] = q0, s_red[tid][s1] = q1, s_red[tid][s2] = q2;
     }
@@ -303,18 +445,18 @@ __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q
 // One packed array A of the tile: load, transform along y, then either park its values or
 // complete record fields.  A is a compile-time constant, the format test is CTA-uniform and
 // sits outside the element loops.
+template <int N, int T, int A, bool RVZEL, bool ACC>
+__device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, float *keep, const cplx *__restrict__ tw,
+                                            const EmitParams &ep, const RecLayout &L, unsigned char *rec0, long long z, int x,
+                                            int tid, int p, int b, double (*s_red)[8]);
+
 template <int N, int T, int A, bool SLAB, bool RVZEL>
 __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const cplx *__restrict__ next, const SlabGeom &sg, int zl,
                                            cplx *S, float *keep,
                                            const cplx *__restrict__ tw, const EmitParams &ep, const RecLayout &L,
                                            unsigned char *rec0, long long z, int x,
                                            int tid, int p, int b, bool first, double (*s_red)[8]) {
-    constexpr int M  = N / 16;
-    constexpr int NT = T * M;
-    const int rb = ep.record_bytes, dbl = L.dbl;
-    constexpr bool rvzel = RVZEL;
-    const bool qplt = ep.qPLT;
-    const double vn = ep.vnorm;
+    constexpr int M = N / 16;
     cplx v[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) {
@@ -331,6 +473,22 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
         }
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
+    emit_finish<N, T, A, RVZEL, false>(v, zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, s_red);
+}
+
+// Transform one packed array of the tile along y (v[e] = row b + M*e on entry), then either park its values or
+// complete record fields.  `keep` is 64 KB of parking space private to the CTA: shared memory in the
+// one-tile-per-CTA kernel, an L2-resident global area in the persistent ring kernel.
+template <int N, int T, int A, bool RVZEL, bool ACC>
+__device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, float *keep, const cplx *__restrict__ tw,
+                                            const EmitParams &ep, const RecLayout &L, unsigned char *rec0, long long z, int x,
+                                            int tid, int p, int b, double (*s_red)[8]) {
+    constexpr int M  = N / 16;
+    constexpr int NT = T * M;
+    const int rb = ep.record_bytes, dbl = L.dbl;
+    constexpr bool rvzel = RVZEL;
+    const bool qplt = ep.qPLT;
+    const double vn = ep.vnorm;
     b = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // from here on b is the OUTPUT slot
     double *keepd = reinterpret_cast<double *>(keep);  // the same 64 KB seen as [16][NT] doubles (non-RVZel formats)
     if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]: parked until A1 completes the displacement
@@ -341,7 +499,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
                 var += v[e].x * v[e].x;
                 mp = fmax(mp, v[e].y), mn = fmax(mn, -v[e].y);
             }
-            fold_stats<NT>(s_red, tid, var, 0, mp, 1, mn, 4);
+            fold_stats<NT, ACC>(s_red, tid, var, 0, mp, 1, mn, 4);
         }
         if (ep.dens != nullptr) {  // density planes (reference src/output.cpp:196,217-224): float(Re A0)
             float *dp = ep.dens + ((size_t) (zl - ep.z0) * N) * N + x;
@@ -374,8 +532,8 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
                 mp1 = fmax(mp1, v[e].x), mn1 = fmax(mn1, -v[e].x);
                 mp2 = fmax(mp2, v[e].y), mn2 = fmax(mn2, -v[e].y);
             }
-            fold_stats<NT>(s_red, tid, mp1, 2, mn1, 5, mp2, 3);
-            fold_stats<NT>(s_red, tid, mn2, 6, 0.0, 7, 0.0, 7);
+            fold_stats<NT, ACC>(s_red, tid, mp1, 2, mn1, 5, mp2, 3);
+            fold_stats<NT, ACC>(s_red, tid, mn2, 6, 0.0, 7, 0.0, 7);
         }
         if (ep.out == nullptr) {
             // density-only run: nothing to store
@@ -523,6 +681,108 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     }
 }
 
+// Persistent, ring-prefetched form of the y pass + emission (single GPU): the CTA walks (tile, array)
+// units; while one array of a tile is transformed and its record fields are formed, KP of the 16 slices of
+// the next unit — the next array of the tile, or the first array of the CTA's next tile — land in shared
+// memory through the TMA unit (see fft_tile_ring_kernel).  The 64 KB of parked values move from shared
+// memory to an L2-resident global area to make room for the ring.
+#define ZPLT_KEEP_BYTES 65536
+template <int N, int T, bool RVZEL, int KP>
+__global__ void __launch_bounds__(T *(N / 16), 1)
+   fft_emit_ring_kernel(const cplx *__restrict__ cube, long long z_first, long long nz, EmitParams ep, const cplx *__restrict__ tw,
+                        unsigned int *__restrict__ counter, float *__restrict__ keep_all, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem_ring[];
+    __shared__ double s_red[32][8];
+    constexpr int M  = N / 16;
+    constexpr int NT = T * M;
+    constexpr int XT = N / T;
+    cplx *S            = reinterpret_cast<cplx *>(smem_ring);
+    cplx *L            = reinterpret_cast<cplx *>(smem_ring + RingSmem<N, T>::EXCHANGE);  // [KP][M][T]
+    uint64_t *mbar     = reinterpret_cast<uint64_t *>(smem_ring + RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx));
+    unsigned int *s_nn = reinterpret_cast<unsigned int *>(mbar + 1);
+    float *keep        = keep_all + (size_t) smid() * (ZPLT_KEEP_BYTES / sizeof(float));
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    const unsigned int ntiles = (unsigned int) (XT * nz);
+    const RecLayout Lr = rec_layout(ep.icformat);
+    const long long N3 = (long long) N * N * N;
+    const bool qplt    = ep.qPLT;
+    auto issue_ring = [&](unsigned int t, int a) {
+        if (tid == 0) {
+            mbar_expect_tx(mbar, (unsigned) (KP * M * T * sizeof(cplx)));
+            const int tx = t % XT, zl = (int) z_first + (int) (t / XT);
+#pragma unroll
+            for (int e = 0; e < KP; e++) tma_load_4d(L + (size_t) e * M * T, &tmap, tx * 2 * T, M * e, zl, a, mbar);
+        }
+    };
+    for (int i = tid; i < 32 * 8; i += NT) (&s_red[0][0])[i] = 0.0;
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        s_nn[0] = atomicAdd(counter, 1u);
+        s_nn[1] = atomicAdd(counter, 1u);
+    }
+    __syncthreads();
+    unsigned int cur = s_nn[0], nxt = s_nn[1], nn = 0;
+    __syncthreads();
+    if (cur < ntiles) issue_ring(cur, 0);
+    unsigned int parity = 0;
+    while (cur < ntiles) {
+        if (tid == 0) s_nn[0] = atomicAdd(counter, 1u);  // the tile after next
+        const int x        = (int) (cur % XT) * T + p;
+        const long long zl = z_first + cur / XT;
+        const cplx *src    = cube + zl * N * (long long) N + x;
+        unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;
+        // one unit: array A of this tile; NEXT_T / NEXT_A name the unit whose slices are requested meanwhile
+#define ZPLT_UNIT(A, NEXT_OK, NEXT_T, NEXT_A)                                                                          \
+    {                                                                                                                  \
+        cplx v[16];                                                                                                    \
+        _Pragma("unroll") for (int e = KP; e < 16; e++) v[e] = ld_stream(&src[(long long) (A) * N3 + (long long) (b + M * e) * N]); \
+        mbar_wait(mbar, parity);                                                                                       \
+        parity ^= 1u;                                                                                                  \
+        _Pragma("unroll") for (int e = 0; e < KP; e++) v[e] = L[(size_t) (e * M + b) * T + p];                          \
+        __syncthreads(); /* ring consumed; the previous unit's last exchange read is complete */                      \
+        if ((A) == 0) nn = s_nn[0];                                                                                    \
+        if (NEXT_OK) issue_ring(NEXT_T, NEXT_A);                                                                       \
+        emit_finish<N, T, A, RVZEL, true>(v, (int) zl, S, keep, tw, ep, Lr, rec0, zl, x, tid, p, b, s_red);            \
+    }
+        if constexpr (RVZEL) {
+            // RVZel: A0 and A2 first (two parked floats), then A1 and A3 complete the two 16-byte halves
+            if (qplt) {
+                ZPLT_UNIT(0, true, cur, 2)
+                ZPLT_UNIT(2, true, cur, 1)
+                ZPLT_UNIT(1, true, cur, 3)
+                ZPLT_UNIT(3, nxt < ntiles, nxt, 0)
+            } else {
+                ZPLT_UNIT(0, true, cur, 1)
+                ZPLT_UNIT(1, nxt < ntiles, nxt, 0)
+            }
+        } else {
+            if (qplt) {
+                ZPLT_UNIT(0, true, cur, 1)
+                ZPLT_UNIT(1, true, cur, 2)
+                ZPLT_UNIT(2, true, cur, 3)
+                ZPLT_UNIT(3, nxt < ntiles, nxt, 0)
+            } else {
+                ZPLT_UNIT(0, true, cur, 1)
+                ZPLT_UNIT(1, nxt < ntiles, nxt, 0)
+            }
+        }
+#undef ZPLT_UNIT
+        cur = nxt;
+        nxt = nn;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        constexpr int NW = NT / 32;
+        double a7 = s_red[0][tid];
+        for (int w = 1; w < NW; w++) a7 = (tid == 0) ? a7 + s_red[w][tid] : fmax(a7, s_red[w][tid]);
+        double *slot = ep.stats + 8 * (blockIdx.x % ZPLT_STAT_SLOTS);
+        if (tid == 0)
+            atomicAdd(&slot[0], a7);
+        else
+            atomicMax(reinterpret_cast<unsigned long long *>(&slot[tid]), (unsigned long long) __double_as_longlong(a7));
+    }
+}
+
 // ------------------------------------------------------------------ dispatch -------
 static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
@@ -558,8 +818,81 @@ static int persistent_ctas(const void *func, int threads, size_t smem) {
     return sms * per_sm;
 }
 
+static unsigned int *tile_counter(cudaStream_t st) {
+    // one 4-byte work counter per launch, rotating through a small device array so that launches in flight on
+    // different streams never share one
+    static unsigned int *ctr[16] = {nullptr};
+    static int next[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return nullptr;
+    if (!ctr[dev] && cudaMalloc((void **) &ctr[dev], 64 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    unsigned int *c = ctr[dev] + (next[dev]++ & 63);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
+    return c;
+}
+
+// 4-D FP64 tensor map (no swizzle, no interleave) through the driver entry point; 0 on success
+static int encode_tmap4(CUtensorMap *tmap, const void *base, const cuuint64_t dims[4], const cuuint64_t strides[3],
+                        const cuuint32_t box[4]) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return (int) cudaErrorNotSupported;
+        encode = (encode_fn) fn;
+    }
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return (int) cudaErrorInvalidValue;
+    return 0;
+}
+
+template <int N, int T, int KP>
+static int launch_tiles_ring_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
+    constexpr int M = N / 16;
+    const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 16;
+    cudaError_t e = cudaFuncSetAttribute(fft_tile_ring_kernel<N, T, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    unsigned int *ctr = tile_counter(st);
+    if (!ctr) return (int) cudaErrorMemoryAllocation;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (long long) g.grid_x * g.grid_y * g.grid_z;
+    if (ntiles >= (1ll << 31)) return (int) cudaErrorInvalidValue;
+    const long long nctas = ntiles < sms ? ntiles : sms;
+    // the data as a 4-D tensor of doubles: (x, rows of the outer index, transform axis, array)
+    CUtensorMap tmap;
+    const cuuint64_t dims[4]    = {(cuuint64_t) 2 * T * g.grid_x, (cuuint64_t) g.grid_y, (cuuint64_t) N, (cuuint64_t) g.grid_z};
+    const cuuint64_t astr       = g.grid_z > 1 ? (cuuint64_t) g.astride : (cuuint64_t) g.nstride * N;
+    const cuuint64_t ostr       = g.grid_y > 1 ? (cuuint64_t) g.ostride : (cuuint64_t) g.nstride * N;  // extent-1 axes: any valid stride
+    const cuuint64_t strides[3] = {ostr * sizeof(cplx), (cuuint64_t) g.nstride * sizeof(cplx), astr * sizeof(cplx)};
+    const cuuint32_t box[4]     = {2 * T, 1, (cuuint32_t) M, 1};
+    if (int rc = encode_tmap4(&tmap, data, dims, strides, box)) return rc;
+    fft_tile_ring_kernel<N, T, KP><<<(unsigned) nctas, T *(N / 16), smem, st>>>(data, g, tw, ctr, tmap);
+    return (int) cudaGetLastError();
+}
+
 template <int N, int T>
 static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
+    // ring-prefetched variant for unit-stride tiles (the z pass and the plain y pass); ZPLT_ZRING = slices to prefetch
+    if constexpr ((N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32)) {
+        const int kp = env_int("ZPLT_ZRING", 12);  // measured at PPD=1024: z pass 33.9 ms without, 29.9 / 28.1 / 27.5 ms with 4 / 8 / 12 slices
+        if (kp > 0 && g.plo_stride == 1 && g.pa == T && g.tstride == T && g.phi_stride == 0) {
+            if constexpr (N == 1024) {
+                if (kp < 8) return launch_tiles_ring_t<N, T, 4>(data, g, tw, st);
+                if (kp < 12) return launch_tiles_ring_t<N, T, 8>(data, g, tw, st);
+            }
+            return launch_tiles_ring_t<N, T, 12>(data, g, tw, st);
+        }
+    }
     size_t smem = fft_tile_smem(N, T);
     cudaError_t e = cudaFuncSetAttribute(fft_tile_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
@@ -663,9 +996,47 @@ int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &g, const cplx *tw
     return (int) cudaErrorInvalidValue;
 }
 
+template <int N, int T, bool RVZEL, int KP>
+static int launch_emit_ring_t(const cplx *cube, int na, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
+                              cudaStream_t st) {
+    constexpr int M = N / 16;
+    const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 16;
+    cudaError_t e = cudaFuncSetAttribute(fft_emit_ring_kernel<N, T, RVZEL, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    unsigned int *ctr = tile_counter(st);
+    if (!ctr) return (int) cudaErrorMemoryAllocation;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (long long) (N / T) * nz;
+    const long long nctas  = ntiles < sms ? ntiles : sms;
+    // the cube [a][z][y][x] as a tensor of doubles (x, y = transform axis, z, a)
+    CUtensorMap tmap;
+    const cuuint64_t dims[4]    = {(cuuint64_t) 2 * N, (cuuint64_t) N, (cuuint64_t) N, (cuuint64_t) na};
+    const cuuint64_t strides[3] = {(cuuint64_t) N * sizeof(cplx), (cuuint64_t) N * N * sizeof(cplx), (cuuint64_t) N * N * N * sizeof(cplx)};
+    const cuuint32_t box[4]     = {2 * T, (cuuint32_t) M, 1, 1};
+    if (int rc = encode_tmap4(&tmap, cube, dims, strides, box)) return rc;
+    float *keep_all = reinterpret_cast<float *>(static_cast<unsigned char *>(ep.scratch) + ZPLT_SCRATCH_PARK_BYTES);
+    fft_emit_ring_kernel<N, T, RVZEL, KP><<<(unsigned) nctas, T *(N / 16), smem, st>>>(cube, z_first, nz, ep, tw, ctr, keep_all, tmap);
+    return (int) cudaGetLastError();
+}
+
 template <int N, int T>
 static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long z_first, long long nz, const EmitParams &ep,
                                  const cplx *tw, cudaStream_t st, int *launches) {
+    if constexpr ((N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32)) {
+        // persistent ring-prefetched form (single GPU, records wanted, parking space present); ZPLT_YRING=0 disables
+        if (sg.G == 1 && ep.out != nullptr && ep.scratch != nullptr && env_int("ZPLT_YRING", 12) > 0) {
+            // measured at PPD=1024: RVZel qPLT 28.9 -> 28.4 ms, ZA 20.5 -> 19.3 ms; the double formats lose (RVdoubleZel
+            // 58.0 -> 66.9 ms: the ring kernel's record bursts spill registers), so they keep the one-tile-per-CTA kernel
+            if (ep.icformat == 1 || env_int("ZPLT_YRING", 12) > 100) {
+                int rc = (ep.icformat == 1) ? launch_emit_ring_t<N, T, true, 12>(cube, ep.na, z_first, nz, ep, tw, st)
+                                            : launch_emit_ring_t<N, T, false, 12>(cube, ep.na, z_first, nz, ep, tw, st);
+                if (launches) *launches += 1;
+                return rc;
+            }
+        }
+    }
     size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
     dim3 grid(N / T, (unsigned) nz, 1);
     const bool slab = sg.G > 1, rvzel = ep.icformat == 1;

@@ -35,6 +35,10 @@ struct EmitParams {
     void *scratch;      // per-SM, L2-resident parking space [sm][16][threads] x 24 B (qPLT, one CTA per SM), or NULL
 };
 #define ZPLT_STAT_SLOTS 64
+// EmitParams::scratch: [256 SMs][16][512 threads] x 24 B of record parking, then [256 SMs] x 64 KB that replace the
+// shared-memory parking area in the persistent ring emission kernel
+#define ZPLT_SCRATCH_PARK_BYTES ((size_t) 256 * 16 * 512 * 24)
+#define ZPLT_SCRATCH_BYTES (ZPLT_SCRATCH_PARK_BYTES + (size_t) 256 * 65536)
 
 int fft_tile_T(int N);            // pencils per CTA used for length N (strided / row kernels)
 int gen_xfft_T(int N, int na);    // pencils per CTA of the generation + x-FFT kernel
