@@ -395,7 +395,7 @@ def main_b200(args, rank, world, local_rank):
                        "l2": f"inputs larger than L2 ({16 * na * N**3 / 1e9:.1f} GB spectral arrays streamed per pass)"},
             "stage_ms": dict(zip(names, stage)),
             "stage_gbs": {n: alg_bytes[i] / (stage[i] * 1e-3) / 1e9 for i, n in enumerate(names)},
-            "roofline": {"bound": "hbm", "kernel": ("fft_tile_kernel" if dom == 1 else "fft_emit_strided_kernel") + f" ({names[dom]})", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("fft_tile_ring_kernel" if dom == 1 else "fft_emit_strided_kernel") + f" ({names[dom]})", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes[dom]},
             "clocks": clocks, "gpu_launches": launches,
