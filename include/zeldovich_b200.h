@@ -61,6 +61,9 @@ typedef struct zplt_config {
     int32_t device;       /* CUDA device ordinal, or -1 for the current device */
     int32_t rank;         /* slab decomposition: this context's rank ... */
     int32_t nranks;       /* ... of nranks (1 = whole problem on this GPU) */
+    double f_NL;          /* ZD_f_NL: local primordial non-Gaussianity (0 = Gaussian); single GPU only */
+    double n_s;           /* ZD_n_s: spectral index of the primordial power (only used with f_NL) */
+    double Omega_M;       /* Omega_M at z = 0 (only used with f_NL) */
 } zplt_config;
 
 typedef struct zplt_ctx zplt_ctx;
@@ -84,6 +87,11 @@ int zplt_set_power_spline(zplt_ctx *ctx, int32_t n, const double *x, const doubl
                           double normalization, double Pk_smooth2);
 /* Power-law branch of PowerSpectrum::power (src/power_spectrum.cpp:233-236). */
 int zplt_set_power_law(zplt_ctx *ctx, double index, double normalization, double Pk_smooth2);
+/* ZD_f_NL only: PowerSpectrum::primordial_norm after Normalize() (reference src/power_spectrum.cpp:221-222),
+ * i.e. P(kmin) / kmin^n_s with kmin the smallest positive k of the input table — the scalar behind
+ * PowerSpectrum::infer_Tk (:268-274) and the M(k, a) factor of src/zeldovich.cpp:377-386.  zplt_power_apply
+ * sets it; callers that use zplt_set_power_spline / _law directly must call this too when f_NL != 0. */
+int zplt_set_primordial(zplt_ctx *ctx, double primordial_norm);
 /* PLT eigenmode table exactly as load_eigmodes reads it (src/zeldovich.cpp:794-830):
  * double[ppd_e][ppd_e][ppd_e/2+1][4].  Required when qPLT != 0. */
 int zplt_set_eigenmodes(zplt_ctx *ctx, int32_t ppd_e, const double *table);
@@ -101,7 +109,9 @@ int zplt_set_stream(zplt_ctx *ctx, void *cuda_stream);
 /* ---- the hot path -------------------------------------------------------------- */
 /* Stage 1+2 of the reference (ZeldovichZ + the y half of ZeldovichXY's 2-D FFT): draw
  * the modes, build the packed spectral arrays, inverse-FFT along z and y.  Leaves the
- * arrays resident in HBM, x axis still in Fourier space.  Asynchronous on the stream. */
+ * arrays resident in HBM, x axis still in Fourier space.  Asynchronous on the stream.
+ * With f_NL != 0 it first runs the reference's potential pass (main, src/zeldovich.cpp:945-960: ZeldovichZ with
+ * gen_phi = 1, ZeldovichXY_Phi :699-790) on one extra ppd^3 complex array owned by the context. */
 int zplt_generate(zplt_ctx *ctx);
 /* Stage 3 (x half of Inverse2dFFT + WriteParticlesSlab): inverse-FFT along x and emit
  * the records of planes z0 .. z0+nz-1 in (z, y, x) order into `device_out`

@@ -162,6 +162,8 @@ typedef struct {
     double Pk_norm, Pk_sigma, Pk_sigma_ratio, Pk_smooth, Pk_scale;
     /* output */
     int icformat; /* 0 Zeldovich, 1 RVZel, 2 RVdoubleZel, 3 ZelSimple (enum order of include/output.h:44-49) */
+    /* local primordial non-Gaussianity (include/parameters.h:59-61) */
+    double f_NL, n_s, Omega_M;
 } zo_config;
 
 typedef struct {
@@ -172,6 +174,10 @@ typedef struct {
     double Rnorm;
     int64_t eig_ppd;
     const double *eig;
+    /* f_NL: smallest positive k of the input table and the primordial normalisation
+     * (src/power_spectrum.cpp:160,180,221-222); phi = the transformed potential, [z][y][x] complex, or NULL */
+    double kmin, primordial_norm;
+    const double *phi;
 } zo_state;
 
 /* ------------------------------------------------------------ P(k) --------- */
@@ -235,13 +241,16 @@ static double zo_sigmaR(zo_state *st, double R) {
  * ks/ps: the raw table rows as sscanf("%lf %lf") delivers them. */
 static void zo_power_setup(zo_state *st, int nrows, const double *ks, const double *ps) {
     st->have_spline = 0;
+    st->kmin        = 1e-4; /* power law: "arbitrary; used by f_NL" (src/power_spectrum.cpp:180) */
     if (!st->c.is_powerlaw) {
         double *xs = (double *) malloc(sizeof(double) * nrows), *ys = (double *) malloc(sizeof(double) * nrows);
         int n = 0;
+        st->kmin = 1.7976931348623157e308;
         for (int i = 0; i < nrows; i++) {
             double k = ks[i], P = ps[i];
             if (k < 0.0 || P < 0.0) continue;
             k *= st->c.Pk_scale;
+            if (k > 0.0 && k < st->kmin) st->kmin = k;
             xs[n] = (k > 0.0) ? log(k) : -1e3;
             ys[n] = log(P);
             n++;
@@ -263,6 +272,8 @@ static void zo_power_setup(zo_state *st, int nrows, const double *ks, const doub
     }
     st->normalization /= st->c.boxsize * st->c.boxsize * st->c.boxsize;
     st->Pk_smooth2 = st->c.Pk_smooth * st->c.Pk_smooth;
+    /* src/power_spectrum.cpp:221-222: T(k) = 1 at the smallest k of the table */
+    st->primordial_norm = zo_power(st, st->kmin) / exp(log(st->kmin) * st->c.n_s);
 }
 
 /* host scalars for boundary tests: out = {normalization, Pk_smooth2, sigmaR(Pk_norm) after normalisation * L^1.5} */
@@ -371,9 +382,20 @@ typedef struct {
     double Dr, Di;   /* density mode */
     double s[3];     /* F,G,H = i * s[c] * D   (src/zeldovich.cpp:432-434) */
     double f;        /* velocity growth factor f (src/zeldovich.cpp:415) */
+    double M;        /* f_NL only: potential -> density factor of this mode */
 } zo_mode;
 
 static inline int zo_wrap(int64_t i, int64_t n) { return (int) (i > n / 2 ? i - n : i); }
+
+/* primordial_power / infer_Tk (src/power_spectrum.cpp:263-274) and the M(k, a) factor between the Bardeen
+ * potential and the density (src/zeldovich.cpp:377-386; 1108.5512 eq. 50).  k2 has the origin's 0 replaced by 1. */
+static double zo_Mfactor(const zo_state *st, double kmag, double k2) {
+    double Tk = 1.0;
+    if (kmag > 0.0) Tk = sqrt(zo_power(st, kmag) / (st->primordial_norm * exp(log(kmag) * st->c.n_s)));
+    double H0 = 100., c = 299792.458;
+    double growth = 1. / (1 + st->c.z_initial);
+    return 2. * growth * c * c * Tk * k2 / (3. * st->c.Omega_M * H0 * H0);
+}
 
 /* The primary mode at signed integer wavevector (kx,ky,kz), ky in [0, ppd/2):
  * mask (src/zeldovich.cpp:350-358), RNG position (SURVEY.md A.2 = the nskip
@@ -392,25 +414,41 @@ static void zo_primary(const zo_state *st, u128 seed_state, int kx, int ky, int 
     int kmax      = (int) ((double) (N / 2) * ikcut + .5);
     double k2     = (kx * kx + ky * ky + kz * kz) * fund2;
     double kmag   = sqrt(k2);
-    if (abs(kx) == kmax || abs(kz) == kmax || abs(ky) == kmax) return;
-    if (!c->corner_modes && k2 >= k2cut) return;
-    if (c->qonemode && !(kx == c->one_mode[0] && ky == c->one_mode[1] && kz == c->one_mode[2])) return;
-
-    u128 off = 2 * ((u128) ky * M * M + (u128) (kz < 0 ? kz + M : kz) * M + (u128) (kx < 0 ? kx + M : kx));
-    u128 s   = zo_jump(seed_state, off);
-    double P = zo_power(st, kmag);
-    double R = zo_one_rand(zo_next(&s));
-    double t = zo_one_rand(zo_next(&s));
-    if (!c->fixed_power)
-        R = sqrt(-P * log(R));
-    else
-        R = sqrt(P);
-    t     = 2 * M_PI * t;
-    m->Dr = R * cos(t);
-    m->Di = R * sin(t);
-    if (m->Dr == 0.0 && m->Di == 0.0) return; /* "D != 0." guard, src/zeldovich.cpp:403 */
-
+    int masked = (abs(kx) == kmax || abs(kz) == kmax || abs(ky) == kmax) || (!c->corner_modes && k2 >= k2cut)
+                 || (c->qonemode && !(kx == c->one_mode[0] && ky == c->one_mode[1] && kz == c->one_mode[2]));
+    if (!masked) {
+        u128 off = 2 * ((u128) ky * M * M + (u128) (kz < 0 ? kz + M : kz) * M + (u128) (kx < 0 ? kx + M : kx));
+        u128 s   = zo_jump(seed_state, off);
+        double P = zo_power(st, kmag);
+        double R = zo_one_rand(zo_next(&s));
+        double t = zo_one_rand(zo_next(&s));
+        if (!c->fixed_power)
+            R = sqrt(-P * log(R));
+        else
+            R = sqrt(P);
+        t     = 2 * M_PI * t;
+        m->Dr = R * cos(t);
+        m->Di = R * sin(t);
+    }
     if (k2 == 0.0) k2 = 1.0;
+    if (c->f_NL != 0.) {
+        /* src/zeldovich.cpp:377-400: with an input potential the density of EVERY mode but the origin, masked or
+         * not, is phi(k) M(k); in the phi-generation pass (st->phi == NULL) the caller divides D by M */
+        m->M = zo_Mfactor(st, kmag, k2);
+        if (st->phi) {
+            if (kx == 0 && ky == 0 && kz == 0) {
+                m->Dr = m->Di = 0.0;
+            } else {
+                int64_t x = kx < 0 ? kx + N : kx, y = ky, z = kz < 0 ? kz + N : kz;
+                const double *ph = st->phi + 2 * ((z * N + y) * N + x);
+                m->Dr = ph[0] * m->M;
+                m->Di = ph[1] * m->M;
+            }
+        }
+    }
+    if (m->Dr == 0.0 && m->Di == 0.0) return; /* "D != 0." guard, src/zeldovich.cpp:403 */
+    if (c->f_NL != 0. && !st->phi) return;     /* phi-generation pass: only D and M are used (:388-394) */
+
     double ik2 = 1. / k2;
     double e[4];
     zo_get_eig(st, kx, ky, kz, N, e);
@@ -551,6 +589,40 @@ void zo_spectral_cube(const zo_config *cfg, int nrows, const double *ks, const d
     const int64_t N = cfg->ppd;
     const int na    = zo_narray(cfg);
     u128 s0         = zo_seed_state((uint64_t) (int64_t) cfg->seed);
+    double *phi     = NULL;
+    if (cfg->f_NL != 0.) {
+        /* main(), src/zeldovich.cpp:945-960: Gaussian potential phi_g(k) = D/M with the Hermitian structure of every
+         * other array (ZeldovichZ with gen_phi = 1, :388-394, :485-503), backward transform, local transformation
+         * phi_g + f_NL phi_g^2 on the REAL part, normalised by ppd^3 (ZeldovichXY_Phi, :744-755), forward transform
+         * (Forward2dFFT :765 + ForwardFFT_Yonly :325) */
+        phi = (double *) malloc(sizeof(double) * 2 * N * N * N);
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+        for (int64_t z = 0; z < N; z++)
+            for (int64_t y = 0; y < N; y++)
+                for (int64_t x = 0; x < N; x++) {
+                    double *o = phi + 2 * ((z * N + y) * N + x);
+                    o[0] = o[1] = 0.0;
+                    if (y == N / 2 || (x == 0 && y == 0 && z == 0)) continue;
+                    int kx = zo_wrap(x, N), ky = zo_wrap(y, N), kz = zo_wrap(z, N);
+                    int conj = (ky < 0) || (ky == 0 && (z > N / 2 || (z == 0 && x > N / 2)));
+                    if (conj) kx = zo_wrap((N - x) % N, N), ky = zo_wrap((N - y) % N, N), kz = zo_wrap((N - z) % N, N);
+                    zo_mode m;
+                    zo_primary(&st, s0, kx, ky, kz, &m);
+                    o[0] = m.Dr / m.M;
+                    o[1] = (conj ? -m.Di : m.Di) / m.M;
+                }
+        zo_fft3_backward(phi, N);
+        const double inv = 1. / N / N / N;
+        for (int64_t i = 0; i < N * N * N; i++) {
+            double p       = phi[2 * i];
+            phi[2 * i]     = (p + cfg->f_NL * p * p) * inv;
+            phi[2 * i + 1] = 0.0;
+        }
+        /* forward transform of a real field = conjugate of its backward transform */
+        zo_fft3_backward(phi, N);
+        for (int64_t i = 0; i < N * N * N; i++) phi[2 * i + 1] = -phi[2 * i + 1];
+        st.phi = phi;
+    }
 #pragma omp parallel for collapse(2) schedule(dynamic, 4)
     for (int64_t z = 0; z < N; z++)
         for (int64_t y = 0; y < N; y++)
@@ -564,6 +636,7 @@ void zo_spectral_cube(const zo_config *cfg, int nrows, const double *ks, const d
                 }
             }
     if (st.have_spline) zo_spline_free(&st.sp);
+    free(phi);
 }
 
 size_t zo_record_bytes(int icformat) {

@@ -46,13 +46,16 @@ class Config(C.Structure):
         ("Pk_smooth", C.c_double),
         ("Pk_scale", C.c_double),
         ("icformat", C.c_int),
+        ("f_NL", C.c_double),
+        ("n_s", C.c_double),
+        ("Omega_M", C.c_double),
     ]
 
 
 def make_config(ppd, boxsize=720.0, seed=12346, k_cutoff=1.0, corner_modes=0, qonemode=0, one_mode=(0, 0, 0), qPLT=0,
                 qPLTrescale=0, PLT_target_z=0.0, z_initial=49.0, f_cluster=1.0, fixed_power=0, is_powerlaw=0,
                 powerlaw_index=1000.0, Pk_norm=8.0, Pk_sigma=0.0210839935761, Pk_sigma_ratio=0.0, Pk_smooth=0.0,
-                Pk_scale=1.0, icformat="RVZel"):
+                Pk_scale=1.0, icformat="RVZel", f_NL=0.0, n_s=1.0, Omega_M=1.0):
     c = Config()
     c.ppd, c.boxsize, c.seed, c.k_cutoff = ppd, boxsize, seed, k_cutoff
     c.corner_modes, c.qonemode = corner_modes, qonemode
@@ -62,6 +65,7 @@ def make_config(ppd, boxsize=720.0, seed=12346, k_cutoff=1.0, corner_modes=0, qo
     c.is_powerlaw, c.powerlaw_index = is_powerlaw, powerlaw_index
     c.Pk_norm, c.Pk_sigma, c.Pk_sigma_ratio, c.Pk_smooth, c.Pk_scale = Pk_norm, Pk_sigma, Pk_sigma_ratio, Pk_smooth, Pk_scale
     c.icformat = ICFORMATS[icformat] if isinstance(icformat, str) else int(icformat)
+    c.f_NL, c.n_s, c.Omega_M = f_NL, n_s, Omega_M
     return c
 
 

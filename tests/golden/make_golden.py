@@ -45,13 +45,23 @@ CASES = {
         dict(NP=16**3, ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="5.0", ICFormat='"RVdoubleZel"', ZD_f_cluster="0.97"), 8),
     "plt16_direct_rvzel": (dict(NP=16**3, ZD_qPLT=1, ZD_qPLT_rescale=0, ICFormat='"RVZel"', CPD=5), 16),
     "za16_fixed_zeldovich": (dict(NP=16**3, ZD_qPk_fix_to_mean=1, ICFormat='"Zeldovich"', ZD_Seed=-7, BoxSize="250.5"), None),
+    # local primordial non-Gaussianity (reference src/zeldovich.cpp:699-790, 945-960); large f_NL so that the phi^2 term is visible
+    "za16_fnl_rvdouble": (dict(NP=16**3, ICFormat='"RVdoubleZel"', ZD_f_NL="5000", ZD_n_s="0.96", Omega_M="0.3"), None),
+    "plt16_fnl_rvzel": (dict(NP=16**3, ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="5.0", ICFormat='"RVZel"', ZD_f_NL="-2000",
+                             ZD_n_s="0.96", Omega_M="0.3"), 8),
 }
 
 
 def main():
     pk = np.load(os.path.join(HERE, "wmap1_pk.npy"))
     out = {}
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases, keep the others' entries
+    if only and os.path.exists(os.path.join(HERE, "cases.json")):
+        with open(os.path.join(HERE, "cases.json")) as f:
+            out = json.load(f)
     for name, (over, eig_ppd) in CASES.items():
+        if only and name not in only:
+            continue
         tmp = tempfile.mkdtemp(prefix="zgold_")
         try:
             synth.write_power_table(os.path.join(tmp, "pk.pow"), pk[:, 0], pk[:, 1])

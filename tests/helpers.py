@@ -59,4 +59,7 @@ def params_to_kwargs(p):
         Pk_smooth=float(g("ZD_Pk_smooth", 0.0)),
         Pk_scale=float(g("ZD_Pk_scale", 1.0)),
         icformat=g("ICFormat").strip('"'),
+        f_NL=float(g("ZD_f_NL", 0.0)),
+        n_s=float(g("ZD_n_s", 1.0)),
+        Omega_M=float(g("Omega_M", 1.0)),
     )

@@ -40,6 +40,8 @@ def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
                 ZD_Pk_scale=repr(float(kw["Pk_scale"])), ICFormat='"%s"' % fmtname, ZD_qonemode=kw.get("qonemode", 0),
                 ZD_one_mode=" ".join(str(v) for v in kw.get("one_mode", (0, 0, 0))),
                 ZD_Pk_filename='"%s"' % os.path.join(tmp, "pk.pow"))
+    if kw.get("f_NL", 0.0) != 0.0:
+        over.update(ZD_f_NL=repr(float(kw["f_NL"])), ZD_n_s=repr(float(kw.get("n_s", 1.0))), Omega_M=repr(float(kw.get("Omega_M", 1.0))))
     if kw["Pk_sigma"] > 0:
         over["ZD_Pk_sigma"] = repr(float(kw["Pk_sigma"]))
     else:
@@ -164,6 +166,9 @@ def test_fft_linearity_and_impulse(pkg):
     dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, f_cluster=0.97, icformat="RVdoubleZel", eig=16),
     dict(ppd=32, qPLT=1, icformat="RVZel", eig=64),
     dict(ppd=32, fixed_power=1, seed=-3),
+    # ZD_f_NL: the density of every mode comes from the transformed potential (no masked site stays zero)
+    dict(ppd=32, f_NL=3000.0, n_s=0.96, Omega_M=0.3),
+    dict(ppd=32, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16, f_NL=-1500.0, n_s=0.96, Omega_M=0.3),
 ])
 def test_spectral_arrays_before_fft(pkg, oracle, case):
     case = dict(case)
@@ -205,6 +210,10 @@ def test_full_path_matches_golden(pkg, oracle, name):
     dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=128),
     dict(ppd=128, k_cutoff=2.0, icformat="Zeldovich"),
     dict(ppd=64, icformat="ZelSimple", boxsize=250.0, seed=77),
+    # local primordial non-Gaussianity (reference src/zeldovich.cpp:699-790, 945-960), interpolated and direct eigenmodes
+    dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16, f_NL=2500.0, n_s=0.96, Omega_M=0.3),
+    dict(ppd=128, icformat="RVdoubleZel", f_NL=-4000.0, n_s=0.97, Omega_M=0.31, k_cutoff=2.0),
+    dict(ppd=256, qPLT=1, icformat="RVZel", eig=256, f_NL=1000.0, n_s=0.96, Omega_M=0.3),
 ])
 def test_full_path_matches_oracle(pkg, oracle, case):
     case = dict(case)

@@ -55,6 +55,9 @@ class Config(C.Structure):
         ("device", C.c_int32),
         ("rank", C.c_int32),
         ("nranks", C.c_int32),
+        ("f_NL", C.c_double),
+        ("n_s", C.c_double),
+        ("Omega_M", C.c_double),
     ]
 
 
@@ -87,7 +90,7 @@ class RunReport(C.Structure):
 # every symbol include/zeldovich_b200.h declares
 EXPORTS = [
     "zplt_create", "zplt_destroy", "zplt_last_error", "zplt_record_bytes", "zplt_narray", "zplt_set_power_spline",
-    "zplt_set_power_law", "zplt_set_eigenmodes", "zplt_workspace_bytes", "zplt_set_workspace", "zplt_set_stream",
+    "zplt_set_power_law", "zplt_set_primordial", "zplt_set_eigenmodes", "zplt_workspace_bytes", "zplt_set_workspace", "zplt_set_stream",
     "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_emit_planes_density", "zplt_fetch_planes_density",
     "zplt_write_outputs", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
     "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
@@ -117,6 +120,7 @@ def lib():
     L.zplt_narray.argtypes = [vp]
     L.zplt_set_power_spline.argtypes = [vp, i32, dp, dp, dp, C.c_double, C.c_double]
     L.zplt_set_power_law.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.zplt_set_primordial.argtypes = [vp, C.c_double]
     L.zplt_set_eigenmodes.argtypes = [vp, i32, dp]
     L.zplt_workspace_bytes.argtypes = [vp]
     L.zplt_workspace_bytes.restype = C.c_size_t
@@ -284,6 +288,9 @@ class Context:
 
     def set_power_law(self, index, normalization, Pk_smooth2):
         _ck(lib().zplt_set_power_law(self._h, index, normalization, Pk_smooth2))
+
+    def set_primordial(self, primordial_norm):
+        _ck(lib().zplt_set_primordial(self._h, float(primordial_norm)))
 
     def set_eigenmodes(self, ppd_e, table):
         t = np.ascontiguousarray(table, dtype=np.float64).reshape(-1)

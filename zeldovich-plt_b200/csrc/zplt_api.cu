@@ -97,6 +97,11 @@ struct zplt_ctx {
     double *stats;
     void *scratch;  // per-SM parking space of the emission kernel (256 SMs x 16 x 512 x 24 B = 50 MB)
     bool have_power, have_eig, generated;
+    // ZD_f_NL: the potential (ppd^3 complex), the M(k) table, PowerSpectrum::primordial_norm
+    cplx *phi;
+    double *mtab;
+    double primordial_norm;
+    bool have_primordial;
     // fetch staging
     unsigned char *stage_dev[2];
     size_t stage_bytes;
@@ -157,6 +162,9 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(ZPLT_EINVAL, "bad rank %d of %d", cfg->rank, cfg->nranks);
     if (cfg->nranks > 1 && ((N / 2) % cfg->nranks || N / (2 * cfg->nranks) < 1))
         return fail(ZPLT_EINVAL, "nranks=%d must divide ppd/2=%lld", cfg->nranks, N / 2);
+    if (cfg->f_NL != 0. && cfg->nranks > 1)
+        return fail(ZPLT_EINVAL, "ZD_f_NL != 0 needs the whole potential on one GPU (nranks = 1)");
+    if (cfg->f_NL != 0. && !(cfg->Omega_M > 0.)) return fail(ZPLT_EINVAL, "ZD_f_NL != 0 needs Omega_M > 0");
 
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
@@ -291,6 +299,8 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     cudaFree(c->tw);
     cudaFree(c->stats);
     cudaFree(c->scratch);
+    cudaFree(c->phi);
+    cudaFree(c->mtab);
     for (int i = 0; i < 2; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
         if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -336,6 +346,14 @@ extern "C" int zplt_set_power_law(zplt_ctx *c, double index, double normalizatio
     return build_power_table(c, 1, index, 0, normalization, Pk_smooth2);
 }
 
+extern "C" int zplt_set_primordial(zplt_ctx *c, double primordial_norm) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (!(primordial_norm > 0.)) return fail(ZPLT_EINVAL, "primordial_norm must be positive");
+    c->primordial_norm = primordial_norm;
+    c->have_primordial = true;
+    return ZPLT_OK;
+}
+
 extern "C" int zplt_set_eigenmodes(zplt_ctx *c, int32_t ppd_e, const double *table) {
     if (!c || !table || ppd_e < 2 || (ppd_e & 1)) return fail(ZPLT_EINVAL, "bad eigenmode table");
     CK(cudaSetDevice(c->device));
@@ -374,6 +392,8 @@ extern "C" int zplt_set_stream(zplt_ctx *c, void *s) {
     return ZPLT_OK;
 }
 
+static TileGeom geom_axis(int N, int na, int axis);
+
 static int ensure_cube(zplt_ctx *c) {
     if (c->cube) return ZPLT_OK;
     cudaError_t e = cudaMalloc((void **) &c->cube, c->cube_bytes);
@@ -389,8 +409,39 @@ static int ready(zplt_ctx *c) {
     if (!c) return fail(ZPLT_EINVAL, "null context");
     if (!c->have_power) return fail(ZPLT_ESTATE, "power spectrum not set");
     if (c->cfg.qPLT && !c->have_eig) return fail(ZPLT_ESTATE, "qPLT set but no eigenmode table given");
+    if (c->cfg.f_NL != 0. && !c->have_primordial) return fail(ZPLT_ESTATE, "ZD_f_NL set but zplt_set_primordial has not been called");
     CK(cudaSetDevice(c->device));
     return ensure_cube(c);
+}
+
+// ZD_f_NL: the reference's potential pass (main, src/zeldovich.cpp:945-960).  Leaves in c->phi the backward transform of
+// phi_g + f_NL phi_g^2 (normalised by ppd^3) and points the generation kernels at it.
+static int run_potential(zplt_ctx *c) {
+    const int N = c->N;
+    if (!c->phi) {
+        cudaError_t e = cudaMalloc((void **) &c->phi, (size_t) N * N * N * sizeof(cplx));
+        if (e != cudaSuccess) {
+            c->phi = nullptr;
+            return fail(ZPLT_ENOMEM, "cudaMalloc of the %zu-byte potential array failed: %s", (size_t) N * N * N * sizeof(cplx),
+                        cudaGetErrorString(e));
+        }
+    }
+    if (!c->mtab) CK(cudaMalloc((void **) &c->mtab, c->ptab_count * sizeof(double)));
+    CK(launch_mfactor_table(c->mtab, c->ptab, c->ptab_count, c->gp.fundamental2, c->primordial_norm, c->cfg.n_s, c->cfg.z_initial,
+                            c->cfg.Omega_M, c->stream));
+    GenParams g = c->gp;
+    g.phi       = nullptr;
+    g.mtab      = c->mtab;
+    CK(launch_generate_phi(g, c->phi, c->stream));
+    const int T = fft_tile_T(N);
+    const int axes[3] = {0, 2, 1};
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < 3; i++) CK(launch_fft_tiles(N, T, c->phi, geom_axis(N, 1, axes[i]), c->tw, c->stream));
+        if (pass == 0) CK(launch_fnl_local(c->phi, N, c->cfg.f_NL, c->stream));
+    }
+    c->gp.phi  = c->phi;
+    c->gp.mtab = c->mtab;
+    return ZPLT_OK;
 }
 
 // ---------------------------------------------------------------- hot path --------
@@ -422,6 +473,10 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
     const bool slab = c->sg.G > 1;
     if (slab && !with_fft) return fail(ZPLT_EINVAL, "spectral introspection is single-GPU only");
     CK(cudaEventRecord(c->ev_gen[0], c->stream));
+    if (c->cfg.f_NL != 0.) {
+        if ((rc = run_potential(c))) return rc;
+        c->launches[0] += 10;
+    }
     const int gt = with_fft ? gen_xfft_T(c->N, c->na) : 0;
     if (slab && c->p2p) {
         // Slab rank with mapped peers: stage 1 runs in groups of rows.  The z pass of group j (NVLink-bound,
@@ -450,14 +505,14 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
     if (gt) {
         // fused: draw the modes and transform the x axis in one kernel
         CK(launch_gen_xfft(c->N, gt, c->gp, c->sg, c->cube, c->tw, c->stream));
-        c->launches[0] = 1;
+        c->launches[0] += 1;
     } else {
         if (slab) return fail(ZPLT_EINVAL, "no fused generation kernel for this size");
         CK(launch_generate(c->gp, c->cube, c->stream));
-        c->launches[0] = 1;
+        c->launches[0] += 1;
         if (with_fft) {
             CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 0), c->tw, c->stream));
-            c->launches[0] = 2;
+            c->launches[0] += 1;
         }
     }
     CK(cudaEventRecord(c->ev_gen[1], c->stream));

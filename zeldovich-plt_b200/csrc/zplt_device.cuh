@@ -83,6 +83,12 @@ struct GenParams {
     int pe;                // eigenmode table ppd
     int eig_direct;        // pe % N == 0 -> direct lookup (reference src/zeldovich.cpp:161-170)
     double eig_scale;      // (double)pe / N
+    // local primordial non-Gaussianity (ZD_f_NL != 0; reference src/zeldovich.cpp:377-400): when phi != NULL the
+    // density of every mode but the origin, masked or not, is conj(phi[z][y][x]) * mtab[m] instead of a draw.  phi
+    // holds the BACKWARD transform of the real field phi_g + f_NL phi_g^2; its conjugate is the forward transform
+    // the reference takes.  mtab[m] = M(k = sqrt(m) * fundamental), the potential -> density factor.
+    const double2 *phi;
+    const double *mtab;
 };
 
 struct Mode {
@@ -211,12 +217,19 @@ __device__ __forceinline__ void primary_mode(const GenParams &g, int x, int y, i
     const int kx = wrap_k(x, g.N, g.half), ky = y, kz = wrap_k(z, g.N, g.half);
     const int n2 = kx * kx + ky * ky + kz * kz;
     m.Dr = m.Di = m.s0 = m.s1 = m.s2 = m.f = 0.0;
-    if (mode_masked(g, kx, ky, kz, n2)) return;
-    u128 s    = mode_rng_state(g, x, y, z);
-    double u1 = u64_to_unit(pcg_next(s));
-    double u2 = u64_to_unit(pcg_next(s));
-    double P  = __ldg(&g.ptab[n2]);
-    box_muller(g, P, u1, u2, m.Dr, m.Di);
+    if (g.phi != nullptr) {
+        if (n2 == 0) return;
+        const double2 ph = g.phi[((size_t) z * g.N + y) * g.N + x];
+        const double M   = __ldg(&g.mtab[n2]);
+        m.Dr = ph.x * M, m.Di = -ph.y * M;
+    } else {
+        if (mode_masked(g, kx, ky, kz, n2)) return;
+        u128 s    = mode_rng_state(g, x, y, z);
+        double u1 = u64_to_unit(pcg_next(s));
+        double u2 = u64_to_unit(pcg_next(s));
+        double P  = __ldg(&g.ptab[n2]);
+        box_muller(g, P, u1, u2, m.Dr, m.Di);
+    }
     if (m.Dr == 0.0 && m.Di == 0.0) return;  // "D != 0." guard (reference src/zeldovich.cpp:403)
     double s0, s1, s2, val;
     eig_factors(g, kx, ky, kz, n2, s0, s1, s2, val);
@@ -285,15 +298,26 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
     const int N = g.N, half = g.half, ky = rc.ky, kz = rc.kz;
     int kx[RUN], n2[RUN];
     bool act[RUN], any = false;
+    const bool from_phi = g.phi != nullptr;  // ZD_f_NL: no mode is masked, the density comes from the potential
 #pragma unroll
     for (int j = 0; j < RUN; j++) {
         kx[j]  = wrap_k(x0 + j, N, half);
         n2[j]  = kx[j] * kx[j] + rc.n2yz;
-        act[j] = !mode_masked(g, kx[j], ky, kz, n2[j]);
+        act[j] = from_phi || !mode_masked(g, kx[j], ky, kz, n2[j]);
         any |= act[j];
         Dr[j] = Di[j] = s0[j] = s1[j] = s2[j] = ff[j] = 0.0;
     }
     if (!any) return;
+    if (from_phi) {
+        const double2 *ph = g.phi + ((size_t) ((kz < 0 ? kz + N : kz)) * N + ky) * N + x0;
+#pragma unroll
+        for (int j = 0; j < RUN; j++) {
+            const double2 v = ph[j];
+            const double M  = __ldg(&g.mtab[n2[j]]);
+            Dr[j] = (n2[j] == 0) ? 0.0 : v.x * M;
+            Di[j] = (n2[j] == 0) ? 0.0 : -v.y * M;
+        }
+    } else {
     // the draws: masked sites consume theirs too, so the run is one walk of the generator.  The only
     // break is between x = N/2 (kx = +N/2) and x = N/2+1 (kx = -N/2+1); runs are aligned, so it can
     // only sit between the first and the second site of a run.
@@ -309,6 +333,7 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
     }
 #pragma unroll
     for (int j = 0; j < RUN; j++) box_muller(g, __ldg(&g.ptab[n2[j]]), u1[j], u2[j], Dr[j], Di[j]);
+    }  // draws
 
     if (!g.qPLT) {
 #pragma unroll
@@ -383,6 +408,19 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
     for (int j = 0; j < RUN; j++) {
         if (!act[j] || (Dr[j] == 0.0 && Di[j] == 0.0)) Dr[j] = Di[j] = s0[j] = s1[j] = s2[j] = ff[j] = 0.0;
     }
+}
+
+// The Gaussian density mode alone (mask + draw), for the phi-generation pass of ZD_f_NL
+// (reference src/zeldovich.cpp:350-375 followed by :388-394).
+__device__ __forceinline__ void primary_density(const GenParams &g, int x, int y, int z, double &Dr, double &Di, int &n2) {
+    const int kx = wrap_k(x, g.N, g.half), ky = y, kz = wrap_k(z, g.N, g.half);
+    n2 = kx * kx + ky * ky + kz * kz;
+    Dr = Di = 0.0;
+    if (mode_masked(g, kx, ky, kz, n2)) return;
+    u128 s    = mode_rng_state(g, x, y, z);
+    double u1 = u64_to_unit(pcg_next(s));
+    double u2 = u64_to_unit(pcg_next(s));
+    box_muller(g, __ldg(&g.ptab[n2]), u1, u2, Dr, Di);
 }
 
 // Packed entries A0..A3 for the primary site and for its conjugate-structured twin

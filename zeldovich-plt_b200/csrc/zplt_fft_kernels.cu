@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     // ---- rows without a single unmasked mode (outside the k_cutoff sphere: 1 - pi/4 of all rows; the Nyquist
     //      row) are zero in every packed array, and so are their transforms: store zeros, skip everything else ----
     {
-        bool any = false;
-        if (y < half) {
+        bool any = (g.phi != nullptr) && y < half;  // ZD_f_NL: the density comes from the potential, nothing is masked
+        if (y < half && !any) {
             const int kz = wrap_k(z, N, half);
 #pragma unroll
             for (int j = 0; j < RUN; j++) {

@@ -105,6 +105,94 @@ int launch_generate(const GenParams &g, cplx *cube, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ ZD_f_NL --------
+// Local primordial non-Gaussianity (reference main, src/zeldovich.cpp:945-960; README "Primordial
+// Non-Gaussianity").  The reference draws the Gaussian density modes, turns them into the Bardeen potential
+// phi_g(k) = D / M(k) (ZeldovichZ with gen_phi = 1, :377-394), transforms to configuration space, applies
+// phi = phi_g + f_NL phi_g^2 (ZeldovichXY_Phi, :699-790), transforms forward and feeds phi(k) M(k) back as
+// the density of every mode (:396-400).  Here: mfactor_table_kernel (M at every |k|^2 the lattice has),
+// generate_phi_kernel, the ordinary in-place FFT passes, fnl_local_kernel, the same passes again (a real
+// field's forward transform is the conjugate of its backward transform), and the generation kernels read
+// GenParams::phi.
+
+// M(k, a) = 2 D(a) c^2 T(k) k^2 / (3 Omega_M H0^2) with T(k) = sqrt(P(k) / (primordial_norm k^n_s)), T(0) = 1
+// (reference src/zeldovich.cpp:377-386, src/power_spectrum.cpp:263-274), same order of operations.
+__global__ void mfactor_table_kernel(double *__restrict__ mtab, const double *__restrict__ ptab, long long count,
+                                     double fundamental2, double primordial_norm, double n_s, double z_initial, double Omega_M) {
+    long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= count) return;
+    double k2   = (double) m * fundamental2;
+    double kmag = sqrt(k2);
+    if (k2 == 0.0) k2 = 1.0;
+    double Tk = 1.0;
+    if (kmag > 0.0) Tk = sqrt(ptab[m] / (primordial_norm * exp(log(kmag) * n_s)));
+    const double H0 = 100., c = 299792.458;
+    const double growth = 1. / (1 + z_initial);
+    mtab[m] = 2. * growth * c * c * Tk * k2 / (3. * Omega_M * H0 * H0);
+}
+
+// phi_g(k) on the full lattice [z][y][x]: D/M at primary sites, its conjugate at their twins, with the
+// Hermitian bookkeeping of every other array (y = 0 plane, origin, Nyquist row: see generate_kernel).
+__global__ void __launch_bounds__(128) generate_phi_kernel(GenParams g, cplx *__restrict__ phi) {
+    const int N = g.N;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.y;
+    const int y = blockIdx.z;  // 0 .. N/2
+    if (x >= N) return;
+    if (y == g.half) {
+        phi[((size_t) z * N + y) * N + x] = make_double2(0.0, 0.0);
+        return;
+    }
+    double Dr, Di;
+    int n2;
+    if (y == 0) {
+        const bool twin = (z > g.half) || (z == 0 && x > g.half);
+        cplx v          = make_double2(0.0, 0.0);
+        if (!(x == 0 && z == 0)) {
+            if (twin)
+                primary_density(g, (N - x) % N, 0, (N - z) % N, Dr, Di, n2);
+            else
+                primary_density(g, x, 0, z, Dr, Di, n2);
+            const double M = __ldg(&g.mtab[n2]);
+            v = make_double2(Dr / M, (twin ? -Di : Di) / M);
+        }
+        phi[((size_t) z * N) * N + x] = v;
+        return;
+    }
+    primary_density(g, x, y, z, Dr, Di, n2);
+    const double M = __ldg(&g.mtab[n2]);
+    phi[((size_t) z * N + y) * N + x] = make_double2(Dr / M, Di / M);
+    const int xh = (N - x) % N, zh = (N - z) % N;
+    phi[((size_t) zh * N + (N - y)) * N + xh] = make_double2(Dr / M, -Di / M);
+}
+
+// phi <- (Re phi + f_NL (Re phi)^2) / ppd^3, imaginary part dropped (reference src/zeldovich.cpp:744-755)
+__global__ void fnl_local_kernel(cplx *__restrict__ phi, long long n, double f_NL, double inv_ppd3) {
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+        const double p = phi[i].x;
+        phi[i]         = make_double2((p + f_NL * p * p) * inv_ppd3, 0.0);
+    }
+}
+
+int launch_mfactor_table(double *mtab, const double *ptab, long long count, double fundamental2, double primordial_norm, double n_s,
+                         double z_initial, double Omega_M, cudaStream_t st) {
+    int threads = 256;
+    mfactor_table_kernel<<<(unsigned) ((count + threads - 1) / threads), threads, 0, st>>>(mtab, ptab, count, fundamental2,
+                                                                                           primordial_norm, n_s, z_initial, Omega_M);
+    return (int) cudaGetLastError();
+}
+int launch_generate_phi(const GenParams &g, cplx *phi, cudaStream_t st) {
+    int threads = g.N < 128 ? g.N : 128;
+    dim3 grid((g.N + threads - 1) / threads, g.N, g.N / 2 + 1);
+    generate_phi_kernel<<<grid, threads, 0, st>>>(g, phi);
+    return (int) cudaGetLastError();
+}
+int launch_fnl_local(cplx *phi, int N, double f_NL, cudaStream_t st) {
+    const double inv = 1. / N / N / N;  // as the reference forms it (src/zeldovich.cpp:706)
+    fnl_local_kernel<<<148 * 8, 256, 0, st>>>(phi, (long long) N * N * N, f_NL, inv);
+    return (int) cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ introspection --
 __global__ void pcg_draws_kernel(const u128 *state0, const Affine *jump, long long n, uint64_t *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;

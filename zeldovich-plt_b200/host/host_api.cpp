@@ -76,7 +76,6 @@ extern "C" int zplt_config_from_params(const zplt_params *p, zplt_config *c) {
     memset(c, 0, sizeof(*c));
     int fmt = zplt_icformat_code(p->ICFormat);
     if (fmt < 0) return hfail(ZPLT_EINVAL, "Error: unknown ICFormat \"%s\". Aborting.", p->ICFormat);
-    if (p->f_NL != 0.) return hfail(ZPLT_EINVAL, "ZD_f_NL != 0 (primordial non-Gaussianity) is outside the B200 hot path");
     if (p->qdensity < 0 || p->qdensity > 2) return hfail(ZPLT_EINVAL, "ZD_qdensity must be 0, 1 or 2");
     c->ppd          = p->ppd;
     c->boxsize      = p->boxsize;
@@ -95,6 +94,9 @@ extern "C" int zplt_config_from_params(const zplt_params *p, zplt_config *c) {
     c->device       = -1;
     c->rank         = 0;
     c->nranks       = 1;
+    c->f_NL         = p->f_NL;
+    c->n_s          = p->n_s;
+    c->Omega_M      = p->Omega_M;
     return ZPLT_OK;
 }
 
@@ -107,6 +109,7 @@ static PkParams pk_params(const zplt_params *p) {
     PkParams q;
     q.boxsize = p->boxsize, q.Pk_scale = p->Pk_scale, q.Pk_norm = p->Pk_norm, q.Pk_sigma = p->Pk_sigma;
     q.Pk_sigma_ratio = p->Pk_sigma_ratio, q.Pk_smooth = p->Pk_smooth, q.qPk_fix_to_mean = p->qPk_fix_to_mean;
+    q.n_s = p->n_s;
     return q;
 }
 
@@ -158,6 +161,10 @@ extern "C" double zplt_power_sigmaR(zplt_power *h, double R) {
 }
 extern "C" int zplt_power_apply(zplt_power *h, zplt_ctx *ctx) {
     if (!h || !ctx) return hfail(ZPLT_EINVAL, "null argument");
+    // the scalar behind infer_Tk; only read by the device when ZD_f_NL != 0
+    if (h->pk.primordial_norm > 0. && std::isfinite(h->pk.primordial_norm)) {
+        if (int rc = zplt_set_primordial(ctx, h->pk.primordial_norm)) return rc;
+    }
     if (h->pk.is_powerlaw) return zplt_set_power_law(ctx, h->pk.powerlaw_index, h->pk.normalization, h->pk.Pk_smooth2);
     return zplt_set_power_spline(ctx, h->pk.size(), h->pk.x.data(), h->pk.y.data(), h->pk.y2.data(), h->pk.normalization,
                                  h->pk.Pk_smooth2);

@@ -115,6 +115,20 @@ void PowerSpectrum::Normalize(const PkParams &param) {
     Pk_smooth2 = param.Pk_smooth * param.Pk_smooth;
     fixed_power = param.qPk_fix_to_mean;
     if (fixed_power) fprintf(stderr, "Fixing density mode amplitudes to sqrt(P(k))\n");
+    // T(k) = 1 at the smallest k of the input (reference src/power_spectrum.cpp:221-222)
+    n_s             = param.n_s;
+    primordial_norm = 1.;
+    primordial_norm = power(kmin) / primordial_power(kmin);
+}
+
+double PowerSpectrum::primordial_power(double wavenumber) {
+    if (wavenumber <= 0.0) return 0.0;
+    return primordial_norm * exp(log(wavenumber) * n_s);
+}
+
+double PowerSpectrum::infer_Tk(double wavenumber) {
+    if (wavenumber <= 0.0) return 1.0;
+    return sqrt(power(wavenumber) / primordial_power(wavenumber));
 }
 
 // reference src/power_spectrum.cpp:225-261

@@ -24,12 +24,12 @@ public:
 
 // the subset of Parameters the power spectrum needs
 struct PkParams {
-    double boxsize, Pk_scale, Pk_norm, Pk_sigma, Pk_sigma_ratio, Pk_smooth;
+    double boxsize, Pk_scale, Pk_norm, Pk_sigma, Pk_sigma_ratio, Pk_smooth, n_s;
     int qPk_fix_to_mean;
-    PkParams() : boxsize(0), Pk_scale(1), Pk_norm(0), Pk_sigma(0), Pk_sigma_ratio(0), Pk_smooth(0), qPk_fix_to_mean(0) {}
+    PkParams() : boxsize(0), Pk_scale(1), Pk_norm(0), Pk_sigma(0), Pk_sigma_ratio(0), Pk_smooth(0), n_s(1), qPk_fix_to_mean(0) {}
     explicit PkParams(const Parameters &p)
         : boxsize(p.boxsize), Pk_scale(p.Pk_scale), Pk_norm(p.Pk_norm), Pk_sigma(p.Pk_sigma), Pk_sigma_ratio(p.Pk_sigma_ratio),
-          Pk_smooth(p.Pk_smooth), qPk_fix_to_mean(p.qPk_fix_to_mean) {}
+          Pk_smooth(p.Pk_smooth), n_s(p.n_s), qPk_fix_to_mean(p.qPk_fix_to_mean) {}
 };
 
 class PowerSpectrum : public SplineFunction {
@@ -37,11 +37,14 @@ public:
     PowerSpectrum();
     int fixed_power, is_powerlaw;
     double powerlaw_index, normalization, Pk_smooth2, Rnorm, kmax, kmin;
+    double n_s, primordial_norm;  // ZD_f_NL: P(kmin) / kmin^n_s (reference src/power_spectrum.cpp:221-222)
 
     int InitFromFile(const fs::path &filename, const PkParams &param);
     int InitFromPowerLaw(double index, const PkParams &param);
     void Normalize(const PkParams &param);
     double power(double wavenumber);
+    double primordial_power(double wavenumber);  // reference src/power_spectrum.cpp:263-266
+    double infer_Tk(double wavenumber);          // reference src/power_spectrum.cpp:268-274
     double sigmaR(double R);
 
 private:
