@@ -376,7 +376,7 @@ def main_b200(args, rank, world, local_rank):
         achieved = alg_bytes[dom] / (stage[dom] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and world == 1:  # the captures are single-GPU launches; a slab rank's launch moves 1/world of it
             try:
                 traffic = json.load(open(tp)).get(f"{names[dom]}@{N}")
             except Exception:

@@ -54,6 +54,40 @@ __device__ __forceinline__ unsigned smid() {
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// L2 residency of the emission kernel's parking areas: they are rewritten for every tile (128 KB per SM, 19 MB in all)
+// while ~160 KB per tile stream past them; without a hint ~9 GB of them per pass were written back to HBM (ncu:
+// 43.3 GB written against 34.4 GB of records).  Parked values are stored and loaded with an evict_last policy.
+__device__ __forceinline__ uint64_t l2_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <bool G>
+__device__ __forceinline__ void park_st(float *p, float v, uint64_t pol) {
+    if constexpr (G)
+        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+    else
+        *p = v;
+}
+template <bool G>
+__device__ __forceinline__ float park_ld(const float *p, uint64_t pol) {
+    if constexpr (G) {
+        float v;
+        asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
+        return v;
+    } else {
+        return *p;
+    }
+}
+__device__ __forceinline__ void park_st2(float2 *p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float2 park_ld2(const float2 *p, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
 // One CTA per tile by default (x tile fastest, so that CTAs running at the same time cover
 // neighbouring 128-byte runs).  Two measured-and-rejected variants stay behind environment
 // switches for experiments: ZPLT_PERSIST=1 (persistent CTAs walking tiles: 36.0 vs 34.6 ms per
@@ -490,6 +524,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
     const bool qplt = ep.qPLT;
     const double vn = ep.vnorm;
     b = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // from here on b is the OUTPUT slot
+    const uint64_t pol = l2_evict_last();
     double *keepd = reinterpret_cast<double *>(keep);  // the same 64 KB seen as [16][NT] doubles (non-RVZel formats)
     if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]: parked until A1 completes the displacement
         {
@@ -509,8 +544,8 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
         if (rvzel) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                keep[(0 * 16 + e) * NT + tid] = (float) v[e].y;
-                if (!qplt) keep[(1 * 16 + e) * NT + tid] = (float) (v[e].y * vn);
+                park_st<ACC>(&keep[(0 * 16 + e) * NT + tid], (float) v[e].y, pol);
+                if (!qplt) park_st<ACC>(&keep[(1 * 16 + e) * NT + tid], (float) (v[e].y * vn), pol);
             }
         } else {
 #pragma unroll
@@ -519,7 +554,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
     } else if (A == 2) {  // Im = vel[0] -> vel[2]: parked until A3 completes the velocity
         if (rvzel) {
 #pragma unroll
-            for (int e = 0; e < 16; e++) keep[(1 * 16 + e) * NT + tid] = (float) v[e].y;
+            for (int e = 0; e < 16; e++) park_st<ACC>(&keep[(1 * 16 + e) * NT + tid], (float) v[e].y, pol);
         } else {
 #pragma unroll
             for (int e = 0; e < 16; e++) keepd[e * NT + tid] = v[e].y;
@@ -547,14 +582,15 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                 if (qplt && ep.scratch != nullptr) {
                     // park (displ0, displ1) in this SM's L2-resident scratch: the record is then written whole, as
                     // two back-to-back 16-byte stores, when A3 is done — no partially written 32-byte sectors in L2
-                    reinterpret_cast<float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid] = make_float2((float) v[e].y, (float) v[e].x);
+                    park_st2(&reinterpret_cast<float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid],
+                             make_float2((float) v[e].y, (float) v[e].x), pol);
                     continue;
                 }
                 *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), (float) v[e].y, (float) v[e].x);
                 if (!qplt)
                     *reinterpret_cast<float4 *>(rec + 16) =
-                       make_float4(keep[(0 * 16 + e) * NT + tid], (float) (v[e].y * vn), (float) (v[e].x * vn),
-                                   keep[(1 * 16 + e) * NT + tid]);
+                       make_float4(park_ld<ACC>(&keep[(0 * 16 + e) * NT + tid], pol), (float) (v[e].y * vn), (float) (v[e].x * vn),
+                                   park_ld<ACC>(&keep[(1 * 16 + e) * NT + tid], pol));
             }
         } else {
             // ids and the whole displacement (and, without qPLT, the whole velocity) in one burst of
@@ -594,12 +630,13 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 if (ep.scratch != nullptr) {
-                    const float2 d01 = reinterpret_cast<const float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid];
+                    const float2 d01 = park_ld2(&reinterpret_cast<const float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid], pol);
                     const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
                     *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), d01.x, d01.y);
                 }
                 *reinterpret_cast<float4 *>(rec + 16) =
-                   make_float4(keep[(0 * 16 + e) * NT + tid], (float) v[e].y, (float) v[e].x, keep[(1 * 16 + e) * NT + tid]);
+                   make_float4(park_ld<ACC>(&keep[(0 * 16 + e) * NT + tid], pol), (float) v[e].y, (float) v[e].x,
+                               park_ld<ACC>(&keep[(1 * 16 + e) * NT + tid], pol));
             }
         } else {
             const double *sd = reinterpret_cast<const double *>(ep.scratch);
