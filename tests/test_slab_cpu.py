@@ -34,6 +34,18 @@ def test_ownership_is_a_partition_with_hermitian_pairs_together(pkg, ppd, G):
     assert pkg.slab_owner(ppd, G, ppd // 2) == (0, h)  # the zero Nyquist row sits in rank 0's spare slot
 
 
+@pytest.mark.parametrize("ppd,G", [(1024, 2), (1024, 8), (2048, 8)])
+def test_ownership_balances_the_unmasked_modes(pkg, ppd, G):
+    """Rows outside the k_cutoff sphere are masked (reference src/zeldovich.cpp:350-358), so the generation work of a
+    primary row ky is ~ the area of the disc kx^2 + kz^2 < (ppd/2)^2 - ky^2; every rank must get the same share."""
+    half = ppd // 2
+    work = np.zeros(G)
+    for y in range(half):
+        r, _ = pkg.slab_owner(ppd, G, y)
+        work[r] += np.pi * (half * half - y * y)
+    assert work.max() / work.min() < 1.05, work / work.mean()  # blocks of rows: 2.2x (G=2) to 8.5x (G=8)
+
+
 def _worker(rank, world, port, ppd, na, q):
     import importlib.util
     import sys

@@ -203,6 +203,8 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     c->sg.N = (int) N, c->sg.G = cfg->nranks, c->sg.rank = cfg->rank, c->sg.h = (int) (N / (2 * cfg->nranks)), c->sg.na = c->na;
     c->sg.log2h = 0;
     while ((1 << c->sg.log2h) < c->sg.h) c->sg.log2h++;
+    c->sg.log2G = 0;
+    while ((1 << c->sg.log2G) < c->sg.G) c->sg.log2G++;
     c->sg.ly0 = 0, c->sg.nly = c->sg.h;
     c->slab_elems = (size_t) c->na * N * N * N / cfg->nranks;
     // one buffer on a single GPU; stage-1 + stage-2 buffers when the grid is slab-decomposed
@@ -692,6 +694,8 @@ extern "C" int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray,
     g.N = (int) ppd, g.G = nranks, g.rank = rank, g.h = (int) (ppd / (2 * nranks)), g.na = narray;
     g.log2h = 0;
     while ((1 << g.log2h) < g.h) g.log2h++;
+    g.log2G = 0;
+    while ((1 << g.log2G) < g.G) g.log2G++;
     g.ly0 = 0, g.nly = g.h;
     if (stage == 1) {  // where rank `rank` (the owner of row y) keeps row (a, z, y) before the exchange
         int r, s;

@@ -259,10 +259,10 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     const int na = g.na;
     const int tid = threadIdx.x, p = tid % NP, b = tid / NP;
     constexpr int half = N / 2;
-    // single GPU: y = 0 .. N/2.  Slab rank: its h primary rows, plus the Nyquist row on rank 0.
+    // single GPU: y = 0 .. N/2.  Slab rank: its h primary rows y = slot*G + rank, plus the Nyquist row on rank 0.
     // (in groups: blockIdx.y counts the group's nly rows; one extra block on rank 0's first group is the Nyquist row)
     const int y = (sg.G == 1) ? (int) blockIdx.y
-                              : ((int) blockIdx.y < sg.nly ? sg.rank * sg.h + sg.ly0 + (int) blockIdx.y : half);
+                              : ((int) blockIdx.y < sg.nly ? (sg.ly0 + (int) blockIdx.y) * sg.G + sg.rank : half);
     const int z = blockIdx.x;
     if (y == 0 && z > half) return;  // produced as the twin row of (0, N-z)
 
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
         if (sg.G == 1)
             return (side == 0) ? ((long long) a * N + z) * N * (long long) N + (long long) y * N
                                : ((long long) a * N + zh) * N * (long long) N + (long long) yh * N;
-        const int ly = (y == half) ? sg.h : y - sg.rank * sg.h;  // slot of the primary row
+        const int ly = (y == half) ? sg.h : (y >> sg.log2G);  // slot of the primary row (cyclic ownership, zplt_slab.h)
         return (side == 0) ? slab_b1_row(sg, a, z, ly) : slab_b1_row(sg, a, zh, (y == 0) ? 0 : sg.h + ly);
     };
     constexpr int RUN = N / NT;  // = 16 / NP

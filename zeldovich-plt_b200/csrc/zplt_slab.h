@@ -1,14 +1,18 @@
 // Slab decomposition layout math, shared by host and device code (single source of truth).
 //
 // G ranks.  Stage 1 (generation, x and z transforms) is sharded over y: rank g owns the
-// h = N/(2G) primary rows y in [g*h, (g+1)*h) and their Hermitian partners N-y, 2h rows in
+// h = N/(2G) primary rows y = g, g+G, g+2G, ... < N/2 and their Hermitian partners N-y, 2h rows in
 // all — the reference keeps +ky and -ky planes together for the same reason
-// (reference src/zeldovich.cpp:558-587, yblock and numblock-1-yblock).  Row y = 0 has no
-// partner; rank 0 uses that free slot for the all-zero Nyquist row y = N/2
+// (reference src/zeldovich.cpp:558-587, yblock and numblock-1-yblock).  The assignment is CYCLIC
+// because the work of a row is not uniform: modes outside the k_cutoff sphere are masked, so a
+// rank holding only high-|ky| rows would draw a fraction of the modes (and transform a fraction of
+// the non-zero rows) that a rank holding low-|ky| rows does — with contiguous blocks of rows the
+// slowest rank of 8 had 8.5x the generation work of the fastest and everybody waited for it.
+// Row y = 0 has no partner; rank 0 uses that free slot for the all-zero Nyquist row y = N/2
 // (reference src/zeldovich.cpp:640-650).
 //
-//   slot s of rank g:  s <  h : y = g*h + s
-//                      s >= h : y = N - (g*h + s - h)      (rank 0, s == h : y = N/2)
+//   slot s of rank g:  s <  h : y = s*G + g
+//                      s >= h : y = N - ((s - h)*G + g)      (rank 0, s == h : y = N/2)
 //
 // Stage-1 buffer (per rank):  B1[z][a][slot][x]            N * na * 2h * N complex
 //   = G contiguous blocks along z, block r = planes z in [r*N/G, (r+1)*N/G): what rank r needs.
@@ -34,6 +38,7 @@ struct SlabGeom {
     int h;     // primary rows per rank = N / (2G)  (a power of two, like N and G)
     int na;    // packed arrays
     int log2h;
+    int log2G;
     // stage 1 can run in groups of primary rows [ly0, ly0+nly) (and their partners' slots
     // h+ly0 ...), so that generating one group overlaps with sending the previous one
     int ly0, nly;
@@ -43,24 +48,24 @@ struct SlabGeom {
 ZPLT_HD void slab_owner(int N, int G, int y, int &rank, int &slot) {
     const int h = N / (2 * G), half = N / 2;
     if (y < half) {
-        rank = y / h;
-        slot = y % h;
+        rank = y % G;
+        slot = y / G;
     } else if (y == half) {
         rank = 0;
         slot = h;
     } else {
         const int yp = N - y;  // 1 .. N/2-1
-        rank = yp / h;
-        slot = h + yp % h;
+        rank = yp % G;
+        slot = h + yp / G;
     }
 }
 
 // the row a slot of a rank holds
 ZPLT_HD int slab_row(int N, int G, int rank, int slot) {
     const int h = N / (2 * G);
-    if (slot < h) return rank * h + slot;
+    if (slot < h) return slot * G + rank;
     if (rank == 0 && slot == h) return N / 2;
-    return N - (rank * h + slot - h);
+    return N - ((slot - h) * G + rank);
 }
 
 // element offsets (in complex numbers) of the start of an x-row
@@ -68,16 +73,16 @@ ZPLT_HD long long slab_b1_row(const SlabGeom &s, int a, int z, int slot) {
     return (((long long) z * s.na + a) * (2 * s.h) + slot) * (long long) s.N;
 }
 ZPLT_HD long long slab_b2_row(const SlabGeom &s, int a, int zl, int y) {
-    // slab_owner() with the divisions by h done as shifts
-    const int half = s.N / 2, hm = s.h - 1;
+    // slab_owner() with the divisions by G done as shifts
+    const int half = s.N / 2, gm = s.G - 1;
     int src, slot;
     if (y < half) {
-        src = y >> s.log2h, slot = y & hm;
+        src = y & gm, slot = y >> s.log2G;
     } else if (y == half) {
         src = 0, slot = s.h;
     } else {
         const int yp = s.N - y;
-        src = yp >> s.log2h, slot = s.h + (yp & hm);
+        src = yp & gm, slot = s.h + (yp >> s.log2G);
     }
     return ((((long long) src * (s.N / s.G) + zl) * s.na + a) * (2 * s.h) + slot) * (long long) s.N;
 }
