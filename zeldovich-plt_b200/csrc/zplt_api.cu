@@ -176,7 +176,6 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     CK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return fail(ZPLT_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
 
-    if (const char *e = getenv("ZPLT_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) atoi(e));
     zplt_ctx *c = new zplt_ctx();
     memset(c, 0, sizeof(*c));
     *partial  = c;

@@ -10,15 +10,8 @@
 #include <cstdlib>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
-#ifndef ZPLT_GENX_TWLOAD
-#define ZPLT_GENX_TWLOAD false  // measured: table-loaded twiddles 35.4 ms vs multiplication tree 34.5 ms
-#endif
-#ifndef ZPLT_LDHINT
-#define ZPLT_LDHINT 1
-#endif
-#ifndef ZPLT_STHINT
-#define ZPLT_STHINT 1
-#endif
+// measured in the generation kernel: table-loaded twiddles 35.4 ms vs multiplication tree 34.5 ms
+#define ZPLT_GENX_TWLOAD false
 #include "zplt_fft.cuh"
 #include "zplt_internal.h"
 
@@ -27,22 +20,10 @@ namespace zplt {
 // streaming (read-once / write-once) global accesses: do not keep the lines in L1
 __device__ __forceinline__ cplx ld_stream(const cplx *p) {
     cplx r;
-#if ZPLT_LDHINT == 1
     asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-#elif ZPLT_LDHINT == 2
-    r = __ldcs(p);
-#else
-    r = *p;
-#endif
     return r;
 }
-__device__ __forceinline__ void st_stream(cplx *p, cplx v) {
-#if ZPLT_STHINT == 1
-    __stcs(p, v);
-#else
-    *p = v;
-#endif
-}
+__device__ __forceinline__ void st_stream(cplx *p, cplx v) { __stcs(p, v); }
 
 // resident CTAs per SM the register budget is tuned for: 512 threads of 128 registers fill an SM
 constexpr int min_ctas(int threads) { return threads >= 512 ? 1 : (512 / threads > 8 ? 8 : 512 / threads); }
@@ -88,51 +69,29 @@ __device__ __forceinline__ float2 park_ld2(const float2 *p, uint64_t pol) {
     return v;
 }
 
-// One CTA per tile by default (x tile fastest, so that CTAs running at the same time cover
-// neighbouring 128-byte runs).  Two measured-and-rejected variants stay behind environment
-// switches for experiments: ZPLT_PERSIST=1 (persistent CTAs walking tiles: 36.0 vs 34.6 ms per
-// pass at PPD=1024 — the hardware CTA scheduler balances better) and ZPLT_PREFETCH=1
-// (prefetch.global.L2 of the next tile during the transform: 44.9 ms — the extra translations
-// of 1024 distinct 2 MB pages per tile cost more than the prefetch saves).  ZPLT_PREFETCH=2
-// skips the transform: the bare load/store pattern of the z pass runs in 23.8 ms (5.8 TB/s,
-// 89 % of the measured copy peak) with 128-byte runs and 46.5 ms with 64-byte runs, i.e. the
-// access pattern is not the limit; the ~11 ms on top are the transform's shared-memory
-// exchanges and FP64 work, serialised against the memory phases of a one-CTA-per-SM kernel.
-// A cp.async landing buffer for the next tile was tried too (12/8/4 of 16 elements prefetched:
-// 36.7/34.9/32.4 ms): the extra shared-memory traffic eats what the prefetch gains.
+// One CTA per tile (x tile fastest, so that CTAs running at the same time cover neighbouring 128-byte runs).  This is the
+// general form — every length, row tiles, slab geometries; the unit-stride passes of the large sizes use the
+// ring-prefetched kernel below.  Measured on this kernel at PPD=1024 before the ring existed (z pass 34.6 ms): persistent
+// CTAs walking tiles 36.0 ms (the hardware CTA scheduler balances better); prefetch.global.L2 of the next tile during the
+// transform 44.9 ms (1024 distinct 2 MB pages per tile: the extra translations cost more than the prefetch saves); the bare
+// load/store pattern without the transform 23.8 ms (5.8 TB/s, 89 % of the measured copy peak) with 128-byte runs and
+// 46.5 ms with 64-byte runs; a cp.async landing buffer for the next tile (12/8/4 of 16 elements: 36.7/34.9/32.4 ms).
 template <int N, int T>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16))) fft_tile_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *S         = reinterpret_cast<cplx *>(smem_raw);
     constexpr int M = N / 16;
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
-    const long long poff = (long long) (p % g.pa) * g.plo_stride + (long long) (p / g.pa) * g.phi_stride;
-    const long long ntiles = (long long) g.grid_x * g.grid_y * g.grid_z;
-    auto tile_base = [&](long long t) {
-        const long long tx = t % g.grid_x, ty = (t / g.grid_x) % g.grid_y, tz = t / ((long long) g.grid_x * g.grid_y);
-        return tz * g.astride + ty * g.ostride + tx * g.tstride + poff;
-    };
-    // lanes that lead a contiguous run of the tile issue the prefetches (all lanes for row tiles)
-    const bool pf_lane = (g.plo_stride != 1) || ((p & 7) == 0);
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const long long base = tile_base(t);
-        cplx v[16];
+    const long long t  = blockIdx.x;
+    const long long tx = t % g.grid_x, ty = (t / g.grid_x) % g.grid_y, tz = t / ((long long) g.grid_x * g.grid_y);
+    const long long base = tz * g.astride + ty * g.ostride + tx * g.tstride + (long long) (p % g.pa) * g.plo_stride
+                           + (long long) (p / g.pa) * g.phi_stride;
+    cplx v[16];
 #pragma unroll
-        for (int e = 0; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
-        // prefetch distance: the tile the CTA that follows this one on the SM will load (about one wave
-        // of CTAs ahead); its rows lie in the 2 MB pages this tile has just touched
-        const long long tpf = t + ((g.prefetch >> 2) > 0 ? (g.prefetch >> 2) : (long long) gridDim.x);
-        if ((g.prefetch & 1) && tpf < ntiles && pf_lane) {
-            const long long nb = tile_base(tpf);
+    for (int e = 0; e < 16; e++) v[e] = ld_stream(&data[base + (long long) (b + M * e) * g.nstride]);
+    const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
 #pragma unroll
-            for (int e = 0; e < 16; e++) prefetch_l2(&data[nb + (long long) (b + M * e) * g.nstride]);
-        }
-        int bo = b;
-        if (!(g.prefetch & 2)) bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // bit 1: memory-pattern-only experiment
-#pragma unroll
-        for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (bo + M * e) * g.nstride], v[e]);
-        __syncthreads();  // the exchange buffer is reused by the next tile
-    }
+    for (int e = 0; e < 16; e++) st_stream(&data[base + (long long) (bo + M * e) * g.nstride], v[e]);
 }
 
 // ------------------------------------------------------------------ ring-prefetched strided pass
@@ -185,7 +144,6 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
                         const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem_ring[];
     constexpr int M  = N / 16;
-    constexpr int NT = T * M;
     static_assert(KP >= 1 && KP <= 16, "slices");
     cplx *S            = reinterpret_cast<cplx *>(smem_ring);
     cplx *L            = reinterpret_cast<cplx *>(smem_ring + RingSmem<N, T>::EXCHANGE);  // [KP][M][T]
@@ -291,6 +249,8 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
                 any |= !mode_masked(g, kx, y, kz, kx * kx + y * y + kz * kz);
             }
         }
+        // (skipping the all-masked 64-element slices of the other rows in the pencil builder was tried: the 16 extra
+        // predicates cost more than the skipped loads save, generation + x pass 31.5 -> 33.7 ms)
         if (!__syncthreads_or(any)) {
             for (int P = 0; P < 2 * na; P++) {
                 const int a = P % na, side = P / na;
@@ -850,8 +810,6 @@ static int persistent_ctas(const void *func, int threads, size_t smem) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem);
     if (per_sm < 1) per_sm = 1;
-    int k = env_int("ZPLT_CTAS_PER_SM", 0);
-    if (k > 0 && k < per_sm) per_sm = k;
     return sms * per_sm;
 }
 
@@ -933,16 +891,8 @@ static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStr
     size_t smem = fft_tile_smem(N, T);
     cudaError_t e = cudaFuncSetAttribute(fft_tile_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    {
-        int cv = env_int("ZPLT_CARVEOUT", -1);
-        if (cv >= 0) cudaFuncSetAttribute(fft_tile_kernel<N, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
-    }
     const long long ntiles = (long long) g.grid_x * g.grid_y * g.grid_z;
-    long long nctas        = (long long) persistent_ctas((const void *) fft_tile_kernel<N, T>, T * (N / 16), smem);
-    if (nctas > ntiles || env_int("ZPLT_PERSIST", 0) == 0) nctas = ntiles;
-    TileGeom g2 = g;
-    g2.prefetch = env_int("ZPLT_PREFETCH", 0);
-    fft_tile_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(data, g2, tw);
+    fft_tile_kernel<N, T><<<(unsigned) ntiles, T *(N / 16), smem, st>>>(data, g, tw);
     return (int) cudaGetLastError();
 }
 

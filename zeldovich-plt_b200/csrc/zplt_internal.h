@@ -18,7 +18,6 @@ struct TileGeom {
     long long plo_stride, phi_stride, nstride;
     int pa;
     int grid_x, grid_y, grid_z;
-    int prefetch;  // prefetch the next tile into L2 while transforming the current one
 };
 
 struct EmitParams {
