@@ -945,7 +945,9 @@ static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *p
     for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
     const long long ntiles = (long long) (N / T) * 2 * sg.nly * sg.na;
     long long nctas = persistent_ctas((const void *) fft_tile_p2p_kernel<N, T>, T * (N / 16), smem);
-    // about two thirds of the SMs keep NVLink saturated and leave room for the overlapped generation kernel
+    // about two thirds of the SMs keep NVLink saturated and leave room for the overlapped generation kernel.  At N = 2048
+    // (4-pencil tiles, 64-byte peer stores) the pass is bound by NVLink's efficiency with 64-byte writes (~355 GB/s per GPU),
+    // not by SMs: 8 GPUs, PPD=2048, 197.5 ms/step with the cap and 207.9 ms without it.
     const int lim = env_int("ZPLT_P2P_CTAS", 96);  // 0: as many as fit
     if (lim > 0 && lim < nctas) nctas = lim;
     if (nctas > ntiles) nctas = ntiles;
