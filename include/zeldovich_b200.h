@@ -219,6 +219,8 @@ int zplt_power_info(const zplt_power *pk, int32_t *n_nodes, double *normalizatio
 int zplt_power_arrays(const zplt_power *pk, double *x, double *y, double *y2);
 double zplt_power_eval(zplt_power *pk, double wavenumber);  /* PowerSpectrum::power */
 double zplt_power_sigmaR(zplt_power *pk, double R);         /* PowerSpectrum::sigmaR */
+double zplt_power_infer_Tk(zplt_power *pk, double wavenumber); /* PowerSpectrum::infer_Tk (src/power_spectrum.cpp:268-274), f_NL */
+double zplt_power_primordial_norm(const zplt_power *pk);    /* PowerSpectrum::primordial_norm (src/power_spectrum.cpp:221-222) */
 /* Hand the spline (or power law) to a device context: calls zplt_set_power_spline/_law. */
 int zplt_power_apply(zplt_power *pk, zplt_ctx *ctx);
 

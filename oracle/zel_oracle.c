@@ -276,6 +276,17 @@ static void zo_power_setup(zo_state *st, int nrows, const double *ks, const doub
     st->primordial_norm = zo_power(st, st->kmin) / exp(log(st->kmin) * st->c.n_s);
 }
 
+/* PowerSpectrum::infer_Tk (src/power_spectrum.cpp:268-274) for boundary tests of the f_NL scalars */
+double zo_infer_Tk(const zo_config *cfg, int nrows, const double *ks, const double *ps, double k) {
+    zo_state st;
+    memset(&st, 0, sizeof(st));
+    st.c = *cfg;
+    zo_power_setup(&st, nrows, ks, ps);
+    double Tk = (k <= 0.0) ? 1.0 : sqrt(zo_power(&st, k) / (st.primordial_norm * exp(log(k) * cfg->n_s)));
+    if (st.have_spline) zo_spline_free(&st.sp);
+    return Tk;
+}
+
 /* host scalars for boundary tests: out = {normalization, Pk_smooth2, sigmaR(Pk_norm) after normalisation * L^1.5} */
 void zo_power_scalars(const zo_config *cfg, int nrows, const double *ks, const double *ps, double *out) {
     zo_state st;

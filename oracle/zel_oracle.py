@@ -88,6 +88,8 @@ def lib():
         L.zo_one_rand.restype = C.c_double
         L.zo_power_scalars.argtypes = [C.POINTER(Config), C.c_int, dp, dp, dp]
         L.zo_power_table.argtypes = [C.POINTER(Config), C.c_int, dp, dp, C.c_int64, dp]
+        L.zo_infer_Tk.argtypes = [C.POINTER(Config), C.c_int, dp, dp, C.c_double]
+        L.zo_infer_Tk.restype = C.c_double
         L.zo_spectral_cube.argtypes = [C.POINTER(Config), C.c_int, dp, dp, C.c_int64, dp, dp]
         L.zo_fft3_backward.argtypes = [dp, C.c_int64]
         L.zo_emit.argtypes = [C.POINTER(Config), dp, C.c_void_p, dp]
@@ -137,6 +139,11 @@ def power_scalars(cfg, pk):
     out = np.zeros(3)
     lib().zo_power_scalars(C.byref(cfg), n, _dp(k), _dp(p), _dp(out))
     return dict(normalization=out[0], Pk_smooth2=out[1], sigma_check=out[2])
+
+
+def infer_Tk(cfg, pk, k):
+    n, kk, p = _table(pk)
+    return lib().zo_infer_Tk(C.byref(cfg), n, _dp(kk), _dp(p), float(k))
 
 
 def power_table(cfg, pk, count):

@@ -133,6 +133,24 @@ def test_host_power_spectrum_matches_oracle(pkg, oracle):
         assert np.all(np.diff(x) > 0) and y2[0] == 0 and y2[-1] == 0
 
 
+def test_host_transfer_function_for_f_nl(pkg, oracle):
+    """PowerSpectrum::infer_Tk / primordial_norm (reference src/power_spectrum.cpp:221-222, 263-274): T(k) = 1 at the
+    smallest k of the table, sqrt(P / (primordial_norm k^n_s)) elsewhere — the host scalar the f_NL kernels consume."""
+    with tempfile.TemporaryDirectory() as tmp:
+        P = pkg.Parameters(write_case(tmp, NP=64**3, ZD_f_NL="100", ZD_n_s="0.96", Omega_M="0.3"))
+        assert P.pod.f_NL == 100.0 and P.pod.n_s == 0.96 and P.pod.Omega_M == 0.3
+        cfg = P.config()
+        assert cfg.f_NL == 100.0 and cfg.n_s == 0.96 and cfg.Omega_M == 0.3
+        pk = pkg.PowerSpectrum(P)
+        k, p = helpers.wmap_pk()
+        kmin = k[k > 0].min()
+        assert abs(pk.infer_Tk(kmin) - 1.0) < 1e-14 and pk.infer_Tk(0.0) == 1.0
+        assert abs(pk.primordial_norm / (pk.power(kmin) / kmin**0.96) - 1) < 1e-13
+        ocfg = oracle.make_config(64, f_NL=100.0, n_s=0.96, Omega_M=0.3)
+        for kk in (1e-3, 0.01, 0.0873, 0.5, 2.0, 7.5):
+            assert abs(pk.infer_Tk(kk) / oracle.infer_Tk(ocfg, (k, p), kk) - 1) < 1e-13
+
+
 def test_host_power_law_and_sigma_ratio(pkg, oracle):
     with tempfile.TemporaryDirectory() as tmp:
         path = write_case(tmp, NP=32**3, ZD_Pk_filename='""', ZD_Pk_powerlaw_index="-2.0", ZD_Pk_sigma=0, ZD_Pk_sigma_ratio="0.5",

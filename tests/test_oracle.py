@@ -104,3 +104,25 @@ def test_oracle_matches_live_reference(oracle):
     for f in ("displ", "vel"):
         for c in range(3):
             assert oracle.field_rel_err(rec[f][:, c], ref[f][:, c]) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(helpers.ROOT, "oracle", "_ref", "zeldovich_ref")), reason="reference binary not built")
+def test_oracle_f_nl_matches_live_reference(oracle):
+    """ZD_f_NL (reference src/zeldovich.cpp:699-790, 945-960): the restatement against a live run of the reference binary."""
+    synth = helpers.load_synth()
+    k, p = helpers.wmap_pk()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_power_table(os.path.join(tmp, "pk.pow"), k, p)
+        synth.write_eigmodes(os.path.join(tmp, "eig.bin"), 16)
+        over = dict(NP=32**3, ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="3.0", ICFormat='"RVdoubleZel"', ZD_Pk_filename='"pk.pow"',
+                    ZD_PLT_filename='"eig.bin"', ZD_Seed=4242, ZD_f_NL="-3000", ZD_n_s="0.965", Omega_M="0.315", ZD_k_cutoff="2.0")
+        synth.write_param(os.path.join(tmp, "c.par"), **over)
+        oracle.run_reference("c.par", cwd=tmp, threads=4)
+        ref = oracle.read_ic_dir(os.path.join(tmp, "ic_out"), 32, 375, "RVdoubleZel")
+    cfg = oracle.make_config(32, seed=4242, qPLT=1, qPLTrescale=1, PLT_target_z=3.0, icformat="RVdoubleZel", f_NL=-3000.0, n_s=0.965,
+                             Omega_M=0.315, k_cutoff=2.0)
+    rec, _ = oracle.run(cfg, (k, p), (16, synth.make_eigmodes(16)))
+    assert np.array_equal(rec["ijk"], ref["ijk"])
+    for f in ("displ", "vel"):
+        for c in range(3):
+            assert oracle.field_rel_err(rec[f][:, c], ref[f][:, c]) < 1e-12

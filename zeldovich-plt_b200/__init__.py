@@ -96,7 +96,7 @@ EXPORTS = [
     "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
-    "zplt_power_sigmaR", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
+    "zplt_power_sigmaR", "zplt_power_infer_Tk", "zplt_power_primordial_norm", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
 ]
 
 _lib = None
@@ -161,6 +161,10 @@ def lib():
     L.zplt_power_eval.restype = C.c_double
     L.zplt_power_sigmaR.argtypes = [vp, C.c_double]
     L.zplt_power_sigmaR.restype = C.c_double
+    L.zplt_power_infer_Tk.argtypes = [vp, C.c_double]
+    L.zplt_power_infer_Tk.restype = C.c_double
+    L.zplt_power_primordial_norm.argtypes = [vp]
+    L.zplt_power_primordial_norm.restype = C.c_double
     L.zplt_power_apply.argtypes = [vp, vp]
     L.zplt_load_eigenmodes_file.argtypes = [vp, C.c_char_p]
     L.zplt_write_ic_files.argtypes = [vp, C.c_char_p, i32]
@@ -221,6 +225,13 @@ class PowerSpectrum:
 
     def sigmaR(self, R):
         return lib().zplt_power_sigmaR(self._h, float(R))
+
+    def infer_Tk(self, k):
+        return lib().zplt_power_infer_Tk(self._h, float(k))
+
+    @property
+    def primordial_norm(self):
+        return lib().zplt_power_primordial_norm(self._h)
 
     def apply(self, ctx):
         _ck(lib().zplt_power_apply(self._h, ctx._h))

@@ -159,6 +159,9 @@ extern "C" double zplt_power_sigmaR(zplt_power *h, double R) {
         return -1.0;
     }
 }
+extern "C" double zplt_power_infer_Tk(zplt_power *h, double k) { return h ? h->pk.infer_Tk(k) : 0.0; }
+extern "C" double zplt_power_primordial_norm(const zplt_power *h) { return h ? h->pk.primordial_norm : 0.0; }
+
 extern "C" int zplt_power_apply(zplt_power *h, zplt_ctx *ctx) {
     if (!h || !ctx) return hfail(ZPLT_EINVAL, "null argument");
     // the scalar behind infer_Tk; only read by the device when ZD_f_NL != 0
