@@ -126,3 +126,45 @@ def test_oracle_f_nl_matches_live_reference(oracle):
     for f in ("displ", "vel"):
         for c in range(3):
             assert oracle.field_rel_err(rec[f][:, c], ref[f][:, c]) < 1e-12
+
+
+# option matrix against live runs of the reference binary: every switch of the mode loop and of the writer the
+# restatement implements (reference src/zeldovich.cpp:350-358, 404-438; src/power_spectrum.cpp:225-261, 349-352; src/output.cpp:78-82)
+LIVE_CASES = {
+    "one_mode": (dict(NP=16**3, ZD_qonemode=1, ZD_one_mode="2 3 -1", ICFormat='"Zeldovich"'), dict(qonemode=1, one_mode=(2, 3, -1), icformat="Zeldovich")),
+    "corner_modes_cutoff": (dict(NP=32**3, ZD_CornerModes=1, ZD_k_cutoff="2.0", ICFormat='"RVZel"'), dict(ppd=32, corner_modes=1, k_cutoff=2.0)),
+    "f_cluster_velocity": (dict(NP=16**3, ZD_f_cluster="0.9", ICFormat='"RVdoubleZel"'), dict(f_cluster=0.9, icformat="RVdoubleZel")),
+    "power_law_smoothed": (dict(NP=16**3, ZD_Pk_filename='""', ZD_Pk_powerlaw_index="-1.5", ZD_Pk_smooth="3.0", ICFormat='"RVdoubleZel"'),
+                           dict(is_powerlaw=1, powerlaw_index=-1.5, Pk_smooth=3.0, icformat="RVdoubleZel")),
+    "sigma_ratio_scale": (dict(NP=16**3, ZD_Pk_sigma=0, ZD_Pk_sigma_ratio="0.02", ZD_Pk_scale="1.3", BoxSize="500", ICFormat='"RVdoubleZel"'),
+                          dict(Pk_sigma=0.0, Pk_sigma_ratio=0.02, Pk_scale=1.3, boxsize=500.0, icformat="RVdoubleZel")),
+    "negative_seed_fixed": (dict(NP=16**3, ZD_Seed=-123456, ZD_qPk_fix_to_mean=1, ICFormat='"RVdoubleZel"'),
+                            dict(seed=-123456, fixed_power=1, icformat="RVdoubleZel")),
+    "f_nl_power_law": (dict(NP=16**3, ZD_Pk_filename='""', ZD_Pk_powerlaw_index="-2.0", ZD_f_NL="800", ZD_n_s="1.0", Omega_M="1.0",
+                            ICFormat='"RVdoubleZel"'),
+                       dict(is_powerlaw=1, powerlaw_index=-2.0, f_NL=800.0, n_s=1.0, Omega_M=1.0, icformat="RVdoubleZel")),
+}
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(helpers.ROOT, "oracle", "_ref", "zeldovich_ref")), reason="reference binary not built")
+@pytest.mark.parametrize("name", sorted(LIVE_CASES))
+def test_oracle_options_match_live_reference(oracle, name):
+    synth = helpers.load_synth()
+    over, kw = LIVE_CASES[name]
+    over, kw = dict(over), dict(kw)
+    k, p = helpers.wmap_pk()
+    ppd = kw.pop("ppd", 16)
+    fmt = kw.get("icformat", "RVZel")
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_power_table(os.path.join(tmp, "pk.pow"), k, p)
+        over.setdefault("ZD_Pk_filename", '"pk.pow"')
+        synth.write_param(os.path.join(tmp, "c.par"), **over)
+        oracle.run_reference("c.par", cwd=tmp, threads=2)
+        ref = oracle.read_ic_dir(os.path.join(tmp, "ic_out"), ppd, 375, fmt)
+    rec, _ = oracle.run(oracle.make_config(ppd, **kw), None if kw.get("is_powerlaw") else (k, p))
+    assert np.array_equal(rec["ijk"], ref["ijk"])
+    for f in ("displ", "vel"):
+        if f in ref.dtype.names:
+            tol = 1e-6 if ref[f].dtype == np.float32 else 1e-12
+            for c in range(3):
+                assert oracle.field_rel_err(rec[f][:, c], ref[f][:, c]) < tol, (name, f, c)
