@@ -462,3 +462,44 @@ def test_full_size_oversampling_property(pkg, oracle):
     assert worst < 2e-7, worst
     big.close()
     small.close()
+
+
+def test_kernel_variants_agree_at_full_size(pkg):
+    """BASELINE full size, the benchmark configuration (PPD=1024 qPLT+rescale RVZel): the ring-prefetched kernels and the
+    256-bit record stores must produce what the plain one-tile-per-CTA kernels produce (same transform code, different data
+    movement) — ids byte for byte, fields to one float32 ulp of the field scale."""
+    import torch
+
+    if torch.cuda.mem_get_info()[0] < (100 << 30):
+        pytest.skip("needs ~75 GB of free device memory")
+    synth = load_synth()
+    eig = (128, synth.make_eigmodes(128))
+    kw = default_kw(ppd=1024, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel")
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    planes = (0, 1, 511, 1023)
+    switches = ("ZPLT_ZRING", "ZPLT_YRING", "ZPLT_WIDE_RECORDS")
+
+    def run(env):
+        saved = {k: os.environ.get(k) for k in switches}
+        for k in switches:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            ctx.generate()
+            return [ctx.fetch_planes(z, 1).copy() for z in planes]
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    ref = run({"ZPLT_ZRING": "0", "ZPLT_YRING": "0", "ZPLT_WIDE_RECORDS": "0"})
+    for env in ({}, {"ZPLT_WIDE_RECORDS": "0"}, {"ZPLT_YRING": "0"}, {"ZPLT_ZRING": "0"}):
+        got = run(dict(env))
+        for a, b in zip(got, ref):
+            assert np.array_equal(a["ijk"], b["ijk"]) and np.all(a["pad"] == 0), env
+            for f in ("displ", "vel"):
+                scale = float(np.abs(b[f]).max())
+                assert float(np.abs(a[f].astype(np.float64) - b[f].astype(np.float64)).max()) <= 2e-7 * scale, (env, f)
+    ctx.close()

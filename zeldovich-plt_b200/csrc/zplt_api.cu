@@ -565,6 +565,11 @@ extern "C" int zplt_emit_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, voi
     ep.stats        = c->stats;
     ep.scratch      = (getenv("ZPLT_EMIT_SCRATCH") && atoi(getenv("ZPLT_EMIT_SCRATCH")) == 0) ? nullptr : c->scratch;
     {
+        // 256-bit record stores: default = on in the ring emission kernel (ZPLT_WIDE_RECORDS=0 forces the two 16-byte halves)
+        const char *e = getenv("ZPLT_WIDE_RECORDS");
+        ep.wide_records = e ? atoi(e) : -1;
+    }
+    {
         const char *e = getenv("ZPLT_EMIT_PREFETCH");
         ep.prefetch = e ? atoi(e) : 1;
     }

@@ -31,6 +31,7 @@ struct EmitParams {
     float *dens;        // optional density planes, float32, (z - z0, y, x) order (ZD_qdensity); NULL: none
     double *stats;      // [ZPLT_STAT_SLOTS][8]: sum dens^2, +max[3], -max[3], pad
     int prefetch;       // L2-prefetch the next packed array of the tile during the transform
+    int wide_records;   // RVZel + qPLT: write each 32-byte record with one 256-bit store; -1 = default (ring kernel only), 0 off, 1 on
     void *scratch;      // per-SM, L2-resident parking space [sm][16][threads] x 24 B (qPLT, one CTA per SM), or NULL
 };
 #define ZPLT_STAT_SLOTS 64
