@@ -233,18 +233,22 @@ def test_full_path_matches_oracle(pkg, oracle, case):
     ctx.close()
 
 
-def test_oversampled_pair_phase_matched(pkg, oracle):
-    """BASELINE config 3: PPD=N and PPD=2N with ZD_k_cutoff=2 carry the same modes."""
+@pytest.mark.parametrize("small", [64, 256])
+def test_oversampled_pair_phase_matched(pkg, oracle, small):
+    """BASELINE config 3 (PPD=256 then PPD=512 with ZD_k_cutoff=2): PPD=N and PPD=2N with ZD_k_cutoff=2 carry the same
+    modes with the same phases, so the ZA displacements of the oversampled run at even sites are those of the small run.
+    (With qPLT only the phases match: the eigenmodes are a function of k relative to each run's own lattice.)"""
     pk = helpers.wmap_pk()
+    big = 2 * small
     recs = {}
-    for ppd, kc in ((64, 1.0), (128, 2.0)):
+    for ppd, kc in ((small, 1.0), (big, 2.0)):
         ctx, P, power = make_ctx(pkg, default_kw(ppd=ppd, k_cutoff=kc, icformat="Zeldovich"), pk, None)
         ctx.generate()
         recs[ppd] = ctx.fetch_planes(0, ppd)
         ctx.close()
-    b = recs[128].reshape(128, 128, 128)[::2, ::2, ::2].reshape(-1)
+    b = recs[big].reshape(big, big, big)[::2, ::2, ::2].reshape(-1)
     for c in range(3):
-        assert oracle.field_rel_err(b["displ"][:, c], recs[64]["displ"][:, c]) < 1e-12
+        assert oracle.field_rel_err(b["displ"][:, c], recs[small]["displ"][:, c]) < 1e-11
 
 
 def test_plane_ranges_and_file_writer(pkg, oracle):
