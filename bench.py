@@ -338,6 +338,22 @@ def main_b200(args, rank, world, local_rank):
             pinned = torch.empty(chunk * plane, dtype=torch.uint8, pin_memory=True)
         x, y, y2 = power.arrays()
         eig_tab = synth.read_eigmodes(P.PLT_filename)[1] if qplt else None
+
+        def pinned_copy(a):
+            # the step's host inputs live in pinned memory (numpy views of pinned torch tensors); pageable if pinning fails
+            try:
+                import numpy as np
+
+                t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                keep_alive.append(t)
+                return t.numpy()
+            except Exception:
+                return a
+
+        keep_alive = []
+        x, y, y2 = pinned_copy(x), pinned_copy(y), pinned_copy(y2)
+        if qplt:
+            eig_tab = pinned_copy(eig_tab)
         h2d = x.nbytes * 3 + (eig_tab.nbytes if qplt else 0)
         nsteps = max(1, min(args.steps, 3))
 
