@@ -344,7 +344,7 @@ def main_b200(args, rank, world, local_rank):
             try:
                 import numpy as np
 
-                t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                t = torch.from_numpy(np.array(a, order="C", copy=True)).pin_memory()
                 keep_alive.append(t)
                 return t.numpy()
             except Exception:
