@@ -73,7 +73,52 @@ def conflicts(N, T, pstride, swz=lambda a: a):
     return total / ideal, detail
 
 
+def conflicts64(N, T, pstride, swz=lambda a: a):
+    """The same exchange patterns with 8-byte elements (the exchange split into a real and an imaginary round — DESIGN.md §9.1):
+    a 64-bit access is served per half-warp, 16 lanes, conflict-free iff their 8-byte words differ mod 16."""
+    M, _, _ = plan(N)
+    NT = T * M
+    total, ideal, detail = 0, 0, []
+    for name, fn in accesses(N, T):
+        lists = {tid: fn(tid // T) for tid in range(NT)}
+        ninstr = len(lists[0])
+        w = 0
+        for q0 in range(0, NT, 16):
+            lanes = list(range(q0, min(q0 + 16, NT)))
+            for i in range(ninstr):
+                banks = {}
+                for tid in lanes:
+                    word = (tid % T) * pstride + swz(lists[tid][i])
+                    banks.setdefault(word % 16, set()).add(word)
+                w += max(len(v) for v in banks.values())
+        nq = (NT + 15) // 16
+        detail.append((name, w / (nq * ninstr)))
+        total += w
+        ideal += nq * ninstr
+    return total / ideal, detail
+
+
+def search64(N, T):
+    """Best (ratio, pencil-stride offset, xor shift) for the 8-byte exchange; shift 0 = no swizzle."""
+    best = None
+    for ps_off in range(0, 17):
+        for sh in range(0, 9):
+            for mask in (1, 3, 7, 15):
+                swz = (lambda a: a) if sh == 0 else (lambda a, sh=sh, mask=mask: a ^ ((a >> sh) & mask))
+                r, d = conflicts64(N, T, N + ps_off, swz)
+                if best is None or r < best[0] - 1e-9:
+                    best = (r, ps_off, sh, mask if sh else 0, d)
+                if sh == 0:
+                    break
+    return best
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[3] == "split":
+        r, off, sh, mask, d = search64(int(sys.argv[1]), int(sys.argv[2]))
+        print(f"8-byte exchange N={sys.argv[1]} T={sys.argv[2]}: best PSTRIDE=N+{off}, swizzle a^((a>>{sh})&{mask}) : "
+              f"avg wavefronts/ideal {r:.3f}  " + " ".join(f"{n}:{v:.2f}" for n, v in d))
+        sys.exit(0)
     N = int(sys.argv[1])
     T = int(sys.argv[2])
     for ps_off in range(0, 9):
