@@ -437,7 +437,7 @@ static int run_potential(zplt_ctx *c) {
     const int T = fft_tile_T(N);
     const int axes[3] = {0, 2, 1};
     for (int pass = 0; pass < 2; pass++) {
-        for (int i = 0; i < 3; i++) CK(launch_fft_tiles(N, T, c->phi, geom_axis(N, 1, axes[i]), c->tw, c->stream));
+        for (int i = 0; i < 3; i++) CK(launch_fft_tiles_any(N, T, c->phi, geom_axis(N, 1, axes[i]), c->tw, c->stream));
         if (pass == 0) CK(launch_fnl_local(c->phi, N, c->cfg.f_NL, c->stream));
     }
     c->gp.phi  = c->phi;
@@ -495,7 +495,7 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
             CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->stream));
             CK(cudaEventRecord(c->ev_group[j], c->stream));
             CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[j], 0));
-            CK(launch_fft_tiles_p2p(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, c->xchg_stream));
+            CK(launch_fft_tiles_p2p_any(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, c->xchg_stream));
         }
         c->launches[0] = J;
         c->launches[1] = J;
@@ -512,7 +512,7 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
         CK(launch_generate(c->gp, c->cube, c->stream));
         c->launches[0] += 1;
         if (with_fft) {
-            CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 0), c->tw, c->stream));
+            CK(launch_fft_tiles_any(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 0), c->tw, c->stream));
             c->launches[0] += 1;
         }
     }
@@ -527,7 +527,7 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
             g.tstride = T, g.grid_x = c->N / T, g.pa = T, g.plo_stride = 1, g.phi_stride = 0;
             g.nstride = (long long) c->na * 2 * c->sg.h * c->N;
         }
-        CK(launch_fft_tiles(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->stream));
+        CK(launch_fft_tiles_any(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->stream));
         c->launches[1] = 1;
     }
     }
@@ -861,7 +861,7 @@ extern "C" int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *
     } else {
         g.nstride = batch, g.plo_stride = 1, g.tstride = T;
     }
-    CK(launch_fft_tiles(n, T, d, g, dtw, 0));
+    CK(launch_fft_tiles_any(n, T, d, g, dtw, 0));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_data, d, bytes, cudaMemcpyDeviceToHost));
     cudaFree(d), cudaFree(dtw);

@@ -1,0 +1,226 @@
+// EXPERIMENTAL — compiled for sm_100a, NOT YET RUN ON A GPU (the round's GPU budget was spent when it was written).
+// Nothing here is reachable unless ZPLT_DIT2048=1 is set; the default paths do not touch this translation unit.
+// First check on a GPU: ZPLT_DIT2048=1 python -m pytest tests -m gpu -k "fft_matches_numpy and 2048" (zplt_dbg_fft goes
+// through launch_fft_tiles_any).  ptxas: 128 registers, ~1.2 KB of spills in both kernels (the combine loop) — to be tuned.
+//
+// 2048-point strided transforms with 8-pencil tiles.  8 pencils x 2048 complex are 256 KB, the whole
+// register file, so the regular kernels fall back to 4-pencil tiles at N = 2048: 64-byte runs, which halve the DRAM
+// efficiency of the strided passes and the NVLink efficiency of the peer stores (measured: 360 GB/s per GPU against
+// 685 GB/s with 128-byte stores).  Here one CTA decimates in time once:
+//   (a) the 1024 even rows of an 8-pencil tile (whole 128-byte rows) -> registers -> 1024-point transform whose
+//       exchanges go through shared memory in a real and an imaginary round (8-byte image: 66 KB instead of 131 KB;
+//       pencil stride N+2 words and index swizzle a ^ ((a >> 2) & 1) make all three passes conflict-free,
+//       `python tools/bank_sim.py 1024 8 split`);
+//   (b) the result E is parked in 128 KB of shared memory — the same thread owns the same output later, no barrier;
+//   (c) the same for the odd rows, O stays in registers;
+//   (d) X[k] = E[k] + W_2048^k O[k],  X[k+1024] = E[k] - W_2048^k O[k], stored as rows k and k+1024 (128-byte runs),
+//       in place or straight into the peers' stage-2 buffers.
+// Replaces, for N = 2048, fft_tile_kernel<2048,4> / fft_tile_p2p_kernel<2048,4> (reference InverseFFT_Yonly,
+// src/zeldovich.cpp:93-114, and BlockArray::StoreBlock/LoadBlock, src/block_array.cpp:387-414, 466-504).
+#include <cstdlib>
+#include <cstring>
+
+#include "zplt_fft.cuh"
+#include "zplt_internal.h"
+
+namespace zplt {
+namespace {
+
+__device__ __forceinline__ cplx ld_stream2(const cplx *p) {
+    cplx r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+struct Split {
+    static constexpr int N = 1024, T = 8, M = 64, R3 = 4;
+    static constexpr int PSTRIDE = N + 2;  // 8-byte words per pencil image
+    static constexpr int NT = T * M;       // 512 threads
+    static constexpr size_t IMAGE_BYTES = (size_t) T * PSTRIDE * sizeof(double);            // 65,664
+    static constexpr size_t PARK_BYTES  = (size_t) 16 * NT * sizeof(cplx);                   // 131,072
+    __device__ static __forceinline__ int at(int a) { return a ^ ((a >> 2) & 1); }
+};
+
+// 1024-point backward transform of one pencil, radices 16 x 16 x 4 as fft_pencil<1024, 8> (zplt_fft.cuh), with every
+// exchange split into a real and an imaginary round through the 8-byte image S.  tw is the W_2048 table, tws = 2 its
+// stride for W_1024.  v[e] = x[b + 64 e] on entry, X[bo + 64 e] on exit; every thread of the CTA must call it, and a CTA
+// barrier must separate two calls (the first exchange of the next call overwrites what pass 3 of this one reads).
+__device__ __forceinline__ int fft1024_split(cplx (&v)[16], double *S, int b, const cplx *__restrict__ tw, int tws) {
+    constexpr int M = Split::M, R3 = Split::R3;
+    // pass 1: radix 16 over stride M
+    dft16(v);
+    {
+        cplx pw[16];
+        twiddle_powers<16>(__ldg(&tw[b * tws]), pw);
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], pw[k]);
+    }
+    const int k1 = b / R3, i = b % R3;
+    const int base = k1 * (16 * R3);
+    // exchange 1: a transpose across the whole pencil (CTA barriers)
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[Split::at(k * M + b)] = v[k].x;
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < 16; n++) v[n].x = S[Split::at(base + n * R3 + i)];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[Split::at(k * M + b)] = v[k].y;
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < 16; n++) v[n].y = S[Split::at(base + n * R3 + i)];
+    // pass 2: radix 16 over stride R3, in place on this thread's own 16 locations
+    dft16(v);
+    {
+        cplx pw[16];
+        twiddle_powers<16>(__ldg(&tw[16 * i * tws]), pw);
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], pw[k]);
+    }
+    // exchange 2: pass 3 only needs what the R3 neighbouring slots of the same warp wrote (warp barriers)
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[Split::at(base + k * R3 + i)] = v[k].x;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16 / R3; j++)
+#pragma unroll
+        for (int n = 0; n < R3; n++) v[j * R3 + n].x = S[Split::at(base + (i + R3 * j) * R3 + n)];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[Split::at(base + k * R3 + i)] = v[k].y;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16 / R3; j++)
+#pragma unroll
+        for (int n = 0; n < R3; n++) v[j * R3 + n].y = S[Split::at(base + (i + R3 * j) * R3 + n)];
+    // pass 3: radix R3 butterflies
+    dft_groups<R3>(v);
+    // butterfly j: v[j*R3 + k] = X[bo + M*(j + (16/R3)*k)]  -> slot order
+    constexpr int NB = 16 / R3;
+    cplx t[16];
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+        for (int k = 0; k < R3; k++) t[j + NB * k] = v[j * R3 + k];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = t[e];
+    return k1 + 16 * i;
+}
+
+// One 8-pencil tile of 2048 points: src + base is element (z = 0) of this thread's pencil, rows are nstride apart;
+// store(z, value) receives the transformed element z of the pencil.
+template <class Store>
+__device__ __forceinline__ void dit2048_tile(const cplx *__restrict__ src, long long base, long long nstride, double *S_pencil, cplx *park,
+                                             const cplx *__restrict__ tw, int tid, int b, Store store) {
+    constexpr int M = Split::M, NT = Split::NT;
+    cplx v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = ld_stream2(&src[base + (long long) (2 * (b + M * e)) * nstride]);
+    __syncthreads();  // the image of the previous transform is no longer read
+    int bo = fft1024_split(v, S_pencil, b, tw, 2);
+#pragma unroll
+    for (int e = 0; e < 16; e++) park[e * NT + tid] = v[e];  // E[bo + 64 e]
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = ld_stream2(&src[base + (long long) (2 * (b + M * e) + 1) * nstride]);
+    __syncthreads();
+    bo = fft1024_split(v, S_pencil, b, tw, 2);  // the same slot permutation: O[bo + 64 e]
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int k  = bo + M * e;
+        const cplx t = cmul(v[e], __ldg(&tw[k]));  // W_2048^k O[k]
+        const cplx E = park[e * NT + tid];
+        store(k, cadd(E, t));
+        store(k + 1024, csub(E, t));
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) fft2048_dit_kernel(cplx *__restrict__ data, TileGeom g, const cplx *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_dit[];
+    double *S  = reinterpret_cast<double *>(smem_dit);
+    cplx *park = reinterpret_cast<cplx *>(smem_dit + Split::IMAGE_BYTES);
+    const int tid = threadIdx.x, p = tid % Split::T, b = tid / Split::T;
+    const long long t  = blockIdx.x;
+    const long long tx = t % g.grid_x, ty = (t / g.grid_x) % g.grid_y, tz = t / ((long long) g.grid_x * g.grid_y);
+    const long long base = tz * g.astride + ty * g.ostride + tx * g.tstride + p;
+    cplx *dst            = data;
+    const long long ns   = g.nstride;
+    dit2048_tile(data, base, ns, S + p * Split::PSTRIDE, park, tw, tid, b, [=](int z, cplx val) { __stcs(&dst[base + (long long) z * ns], val); });
+}
+
+struct PeerTable2 {
+    cplx *recv[16];
+};
+
+// the z pass of a slab rank at N = 2048 with the exchange fused in (see fft_tile_p2p_kernel): 128-byte peer stores
+__global__ void __launch_bounds__(512, 1)
+   fft2048_dit_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, PeerTable2 peers, const cplx *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_dit[];
+    double *S  = reinterpret_cast<double *>(smem_dit);
+    cplx *park = reinterpret_cast<cplx *>(smem_dit + Split::IMAGE_BYTES);
+    constexpr int N = 2048, T = Split::T, XT = N / T;
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    const int rows = sg.na * 2 * sg.h;  // x-rows per z plane of the stage-1 buffer
+    const long long nstride = (long long) rows * N;
+    const int np  = N / sg.G;
+    const int nsl = 2 * sg.nly;
+    const long long ntiles = (long long) XT * nsl * sg.na;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int xt = (int) (t % XT);
+        const int rr = (int) (t / XT), sidx = rr % nsl, a = rr / nsl;
+        const int slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
+        const int row  = a * 2 * sg.h + slot;
+        const int x    = xt * T + p;
+        const long long base = (long long) row * N + x;
+        const int rank = sg.rank;
+        dit2048_tile(b1, base, nstride, S + p * Split::PSTRIDE, park, tw, tid, b, [&](int z, cplx val) {
+            const int r = z / np, zl = z % np;
+            __stcs(&peers.recv[r][(((long long) rank * np + zl) * rows + row) * N + x], val);
+        });
+    }
+}
+
+bool dit2048_enabled() {
+    const char *e = getenv("ZPLT_DIT2048");
+    return e && atoi(e) > 0;
+}
+constexpr size_t DIT_SMEM = Split::IMAGE_BYTES + Split::PARK_BYTES;
+
+}  // namespace
+
+// In-place strided pass with the N = 2048 decimation kernel when it is enabled and the geometry is the 4-pencil
+// unit-stride tiling the regular launcher would use; otherwise the regular launcher.
+int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
+    if (N == 2048 && dit2048_enabled() && g.plo_stride == 1 && g.phi_stride == 0 && g.pa == 4 && g.tstride == 4 && (g.grid_x % 2) == 0) {
+        TileGeom g8 = g;
+        g8.pa = 8, g8.tstride = 8, g8.grid_x = g.grid_x / 2;
+        cudaError_t e = cudaFuncSetAttribute(fft2048_dit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DIT_SMEM);
+        if (e != cudaSuccess) return (int) e;
+        const long long ntiles = (long long) g8.grid_x * g8.grid_y * g8.grid_z;
+        fft2048_dit_kernel<<<(unsigned) ntiles, 512, DIT_SMEM, st>>>(data, g8, tw);
+        return (int) cudaGetLastError();
+    }
+    return launch_fft_tiles(N, T, data, g, tw, st);
+}
+
+int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, cudaStream_t st) {
+    if (N == 2048 && dit2048_enabled() && sg.G <= 16) {
+        cudaError_t e = cudaFuncSetAttribute(fft2048_dit_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DIT_SMEM);
+        if (e != cudaSuccess) return (int) e;
+        PeerTable2 pt;
+        for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long ntiles = (long long) (N / 8) * 2 * sg.nly * sg.na;
+        long long nctas = sms;
+        const char *c = getenv("ZPLT_P2P_CTAS");
+        const int lim = c ? atoi(c) : 96;  // as fft_tile_p2p_kernel: leave SMs to the overlapped generation kernel
+        if (lim > 0 && lim < nctas) nctas = lim;
+        if (nctas > ntiles) nctas = ntiles;
+        fft2048_dit_p2p_kernel<<<(unsigned) nctas, 512, DIT_SMEM, st>>>(b1, sg, pt, tw);
+        return (int) cudaGetLastError();
+    }
+    return launch_fft_tiles_p2p(N, T, b1, sg, peer_recv, tw, st);
+}
+
+}  // namespace zplt

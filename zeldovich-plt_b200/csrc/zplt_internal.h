@@ -51,6 +51,11 @@ int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx 
 // directly into every owner rank's stage-2 buffer (peer_recv[r], NVLink peer memory).
 int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
                          cudaStream_t st);
+// The same two launchers behind a switch: with ZPLT_DIT2048=1 and N = 2048 they use the 8-pencil decimation kernels of
+// zplt_fft2048_kernels.cu (experimental, see that file); otherwise they forward to the launchers above.
+int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
+                             cudaStream_t st);
 // y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
                             const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches);
