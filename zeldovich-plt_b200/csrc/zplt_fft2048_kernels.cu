@@ -2,6 +2,8 @@
 // Nothing here is reachable unless ZPLT_DIT2048=1 is set; the default paths do not touch this translation unit.
 // First check on a GPU: ZPLT_DIT2048=1 python -m pytest tests -m gpu -k "fft_matches_numpy and 2048" (zplt_dbg_fft goes
 // through launch_fft_tiles_any).  ptxas: 128 registers, ~1.2 KB of spills in both kernels (the combine loop) — to be tuned.
+// The index arithmetic (exchange patterns, swizzle, slot permutation, combine) is checked thread by thread in numpy by
+// tools/proto_dit2048.py.
 //
 // 2048-point strided transforms with 8-pencil tiles.  8 pencils x 2048 complex are 256 KB, the whole
 // register file, so the regular kernels fall back to 4-pencil tiles at N = 2048: 64-byte runs, which halve the DRAM
