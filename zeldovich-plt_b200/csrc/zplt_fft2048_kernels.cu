@@ -1,7 +1,7 @@
 // EXPERIMENTAL — compiled for sm_100a, NOT YET RUN ON A GPU (the round's GPU budget was spent when it was written).
 // Nothing here is reachable unless ZPLT_DIT2048=1 is set; the default paths do not touch this translation unit.
 // First check on a GPU: ZPLT_DIT2048=1 python -m pytest tests -m gpu -k "fft_matches_numpy and 2048" (zplt_dbg_fft goes
-// through launch_fft_tiles_any).  ptxas: 128 registers, ~1.2 KB of spills in both kernels (the combine loop) — to be tuned.
+// through launch_fft_tiles_any).  ptxas: 128 registers, no spills (8 bytes in the in-place variant).
 // The index arithmetic (exchange patterns, swizzle, slot permutation, combine) is checked thread by thread in numpy by
 // tools/proto_dit2048.py.
 //
@@ -115,24 +115,28 @@ template <class Store>
 __device__ __forceinline__ void dit2048_tile(const cplx *__restrict__ src, long long base, long long nstride, double *S_pencil, cplx *park,
                                              const cplx *__restrict__ tw, int tid, int b, Store store) {
     constexpr int M = Split::M, NT = Split::NT;
-    cplx v[16];
+    // one inlined copy of the transform, run twice: even rows (h = 0, result parked), then odd rows (h = 1, combined).
+    // (Two inlined copies keep v[] in local memory: ~1.2 KB of spills; this form has none.)
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        cplx v[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = ld_stream2(&src[base + (long long) (2 * (b + M * e)) * nstride]);
-    __syncthreads();  // the image of the previous transform is no longer read
-    int bo = fft1024_split(v, S_pencil, b, tw, 2);
+        for (int e = 0; e < 16; e++) v[e] = ld_stream2(&src[base + (long long) (2 * (b + M * e) + h) * nstride]);
+        __syncthreads();  // the image of the previous transform is no longer read
+        const int bo = fft1024_split(v, S_pencil, b, tw, 2);  // v[e] = E[bo + 64 e] or O[bo + 64 e]: the same slot permutation
+        if (h == 0) {
 #pragma unroll
-    for (int e = 0; e < 16; e++) park[e * NT + tid] = v[e];  // E[bo + 64 e]
+            for (int e = 0; e < 16; e++) park[e * NT + tid] = v[e];
+        } else {
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = ld_stream2(&src[base + (long long) (2 * (b + M * e) + 1) * nstride]);
-    __syncthreads();
-    bo = fft1024_split(v, S_pencil, b, tw, 2);  // the same slot permutation: O[bo + 64 e]
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const int k  = bo + M * e;
-        const cplx t = cmul(v[e], __ldg(&tw[k]));  // W_2048^k O[k]
-        const cplx E = park[e * NT + tid];
-        store(k, cadd(E, t));
-        store(k + 1024, csub(E, t));
+            for (int e = 0; e < 16; e++) {
+                const int k  = bo + M * e;
+                const cplx t = cmul(v[e], __ldg(&tw[k]));  // W_2048^k O[k]
+                const cplx E = park[e * NT + tid];
+                store(k, cadd(E, t));
+                store(k + 1024, csub(E, t));
+            }
+        }
     }
 }
 
