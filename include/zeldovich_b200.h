@@ -44,7 +44,7 @@ extern "C" {
 /* What the kernels need from reference class Parameters (include/parameters.h:14-74)
  * after Parameters::setup() (src/parameters.cpp:97-197). */
 typedef struct zplt_config {
-    int64_t ppd;          /* particles per dimension; power of two, 16..4096 */
+    int64_t ppd;          /* particles per dimension; power of two, 16..2048 (2048 needs nranks >= 4: HBM) */
     double boxsize;       /* BoxSize */
     int64_t seed;         /* ZD_Seed as the reference widens it: (int) sign-extended (src/power_spectrum.cpp:14) */
     double k_cutoff;      /* ZD_k_cutoff >= 1 */
@@ -107,16 +107,20 @@ int zplt_set_workspace(zplt_ctx *ctx, void *device_ptr, size_t bytes);
 int zplt_set_stream(zplt_ctx *ctx, void *cuda_stream);
 
 /* ---- the hot path -------------------------------------------------------------- */
-/* Stage 1+2 of the reference (ZeldovichZ + the y half of ZeldovichXY's 2-D FFT): draw
- * the modes, build the packed spectral arrays, inverse-FFT along z and y.  Leaves the
- * arrays resident in HBM, x axis still in Fourier space.  Asynchronous on the stream.
+/* The 3-D inverse transform is separable, so the axis order is free; it is x, z, y here (the reference does z, then y
+ * and x): generation fuses with the contiguous x rows, and the two strided axes keep 128-byte runs.
+ *
+ * zplt_generate = ZeldovichZ (reference src/zeldovich.cpp:517-601, LoadPlane :278-515) + the row half of Inverse2dFFT:
+ * draw the modes, build the packed spectral arrays and inverse-FFT along x in one kernel, then inverse-FFT along z in
+ * place.  Leaves the arrays resident in HBM with the y axis still in Fourier space.  Asynchronous on the stream.
  * With f_NL != 0 it first runs the reference's potential pass (main, src/zeldovich.cpp:945-960: ZeldovichZ with
  * gen_phi = 1, ZeldovichXY_Phi :699-790) on one extra ppd^3 complex array owned by the context. */
 int zplt_generate(zplt_ctx *ctx);
-/* Stage 3 (x half of Inverse2dFFT + WriteParticlesSlab): inverse-FFT along x and emit
- * the records of planes z0 .. z0+nz-1 in (z, y, x) order into `device_out`
- * (nz*ppd*ppd*record_bytes bytes of device memory, or pinned host memory mapped into
- * the device address space).  Accumulates density_variance and max_disp.  Asynchronous. */
+/* zplt_emit_planes = the column half of Inverse2dFFT (:88-92 as used at :653-658) + WriteParticlesSlab
+ * (src/output.cpp:41-234): inverse-FFT along y and emit the records of planes z0 .. z0+nz-1 in (z, y, x) order into
+ * `device_out` (nz*ppd*ppd*record_bytes bytes of device memory, or pinned host memory mapped into the device address
+ * space).  The arrays are not modified (emission is repeatable).  Accumulates density_variance and max_disp.
+ * Asynchronous. */
 int zplt_emit_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *device_out);
 /* Convenience for host callers: emit planes z0..z0+nz-1 and copy them to `host_out`
  * (pageable or pinned), double-buffered through an internal staging ring.  Synchronous. */
@@ -137,15 +141,23 @@ int zplt_exchange_done(zplt_ctx *ctx);
  * zplt_set_workspace), the caller gathers the handles in rank order (e.g. torch.distributed
  * all_gather) and hands them to zplt_ipc_import.  From then on zplt_generate's z-axis FFT kernel
  * stores its results straight into the owner ranks' receive buffers — no separate all-to-all
- * pass.  The caller still has to synchronise the stream and run a barrier across ranks before
- * zplt_exchange_done(): a rank may only read its planes once every peer has finished writing. */
+ * pass; rows land at their true y, receive buffer = [local z][array][y][x].  Two barriers across ranks belong to
+ * every step, both the caller's (torch.distributed / MPI; see distributed.PeerExchange.begin / .exchange):
+ *   (1) after zplt_generate: synchronise the stream, barrier, then zplt_exchange_done() — a rank may only read its
+ *       planes once every peer has finished writing them;
+ *   (2) before the NEXT zplt_generate: synchronise (emission done), barrier — a peer's z pass of the next step writes
+ *       into the very buffer this rank is still emitting from (write-after-read). */
 int zplt_ipc_export(zplt_ctx *ctx, void *handle64);
 int zplt_ipc_import(zplt_ctx *ctx, int32_t nranks, const void *handles);
+/* Unmap the peers' buffers again.  Every rank must have done so (barrier) before any rank frees its workspace or
+ * destroys its context: freeing memory a peer still has mapped is undefined (CUDA IPC rule). */
+int zplt_ipc_close(zplt_ctx *ctx);
 /* Layout of the decomposition (host mirror of the device index math, for tests and bindings):
  * which rank owns row y in stage 1 and in which of its slots. */
 int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32_t *slot);
 /* Offset, in complex elements, of x-row (a, z, y) inside rank `rank`'s send buffer (stage 1) or
- * receive buffer (stage 2); -1 if that rank does not hold it. */
+ * receive buffer (stage 2, the per-source block layout of the caller-run all-to-all; with the fused exchange the
+ * receive buffer is simply [local z][a][y][x]); -1 if that rank does not hold it. */
 int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray, int32_t stage, int32_t rank, int32_t a, int64_t z, int64_t y);
 
 /* ZD_qdensity (reference src/output.cpp:196,217-224; src/zeldovich.cpp:871-876): the same calls with an
@@ -163,10 +175,15 @@ int zplt_get_stats(zplt_ctx *ctx, double *density_variance, double max_disp[3]);
 /* Block until everything queued on the context's stream has finished. */
 int zplt_synchronize(zplt_ctx *ctx);
 /* Milliseconds the device spent in each stage of the last generate/emit calls
- * (CUDA events on the context's stream): out[0]=mode generation, out[1]=z FFT,
- * out[2]=y FFT, out[3]=x FFT + emission (summed over emit calls since the last generate).
+ * (CUDA events on the context's stream): out[0] = mode generation + x FFT (one fused kernel), out[1] = z FFT (on a
+ * slab rank with mapped peers: 0, the z pass + exchange overlaps out[0] on a second stream and is inside it),
+ * out[2] = 0 (reserved), out[3] = y FFT + emission (summed over emit calls since the last generate).
  * Also out[4..7] = number of kernel launches in each of those stages. */
 int zplt_get_timings(zplt_ctx *ctx, double out[8]);
+/* Tuning / diagnostic switches of a context: "zring", "yring", "wide_records", "emit_scratch", "emit_prefetch",
+ * "slab_groups", "p2p_ctas", "dit2048", "slab_ring", "gen_persist" (csrc/zplt_internal.h, struct Tuning).  Their defaults
+ * come from the environment variables ZPLT_<NAME>, read once in zplt_create — nothing on the launch path calls getenv. */
+int zplt_set_option(zplt_ctx *ctx, const char *name, int32_t value);
 
 /* ---- introspection for parity tests (small sizes; host output buffers) --------- */
 /* n raw pcg64 outputs starting (off_hi*2^64+off_lo) draws after seeding with `seed`,
@@ -177,13 +194,25 @@ int zplt_dbg_pcg_draws(uint64_t seed, uint64_t off_hi, uint64_t off_lo, int64_t 
 int zplt_dbg_mode_draws(zplt_ctx *ctx, int64_t n, const int32_t *k, uint64_t *host_raw, double *host_u);
 /* P(k) at k = sqrt(m)*fundamental for m = 0..count-1, as the mode kernel sees it. */
 int zplt_dbg_power_table(zplt_ctx *ctx, int64_t count, double *host_out);
-/* The packed spectral arrays [narray][z][y][x] (complex double) before any FFT. */
+/* The packed spectral arrays [narray][z][y][x] (complex double) before any FFT, formed by the plain
+ * one-thread-per-mode kernel (zplt_dbg_spectral) or by the hot generation kernel with its transform skipped
+ * (zplt_dbg_spectral_hot: the run walk of the generator, the zero-row skip and the pencil builder of the product path). */
 int zplt_dbg_spectral(zplt_ctx *ctx, double *host_out);
+int zplt_dbg_spectral_hot(zplt_ctx *ctx, double *host_out);
+/* The raw 64-bit draws the HOT generation kernel consumed: host_raw[((z*ppd/2 + y)*ppd + x)*2 + {0,1}] for the primary
+ * half 0 <= y < ppd/2; rows the kernel skips as all-masked stay 0. */
+int zplt_dbg_hot_draws(zplt_ctx *ctx, uint64_t *host_raw);
+/* Same-device stand-ins for the peers of a slab rank (tests of the fused z pass + exchange on one GPU):
+ * recv[r] = device pointer of rank r's receive buffer, NULL = discard that rank's share. */
+int zplt_dbg_set_peers(zplt_ctx *ctx, int32_t nranks, void *const *recv);
 /* The arrays after zplt_generate (z and y transformed, x not yet). */
 int zplt_dbg_after_generate(zplt_ctx *ctx, double *host_out);
 /* Unnormalised backward 1-D FFTs of length n on host data laid out [batch][n]
  * (row_mode=1, contiguous pencils) or [n][batch] (row_mode=0, strided pencils), in place. */
 int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *host_data);
+/* variant 0 = as zplt_dbg_fft (the kernels a default context uses), 1 = the plain one-tile-per-CTA kernels,
+ * 2 = the 8-pencil decimation kernel (n = 2048, strided pencils). */
+int zplt_dbg_fft_variant(int32_t n, int64_t batch, int32_t row_mode, int32_t variant, double *host_data);
 
 
 /* ==== host side of the boundary (C++ implementation, no device work) ================

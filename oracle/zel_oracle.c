@@ -408,6 +408,52 @@ static double zo_Mfactor(const zo_state *st, double kmag, double k2) {
     return 2. * growth * c * c * Tk * k2 / (3. * st->c.Omega_M * H0 * H0);
 }
 
+/* mask of src/zeldovich.cpp:350-358 for the signed integer wavevector (kx,ky,kz); k2 = |k|^2 in physical units */
+static int zo_masked(const zo_config *c, int kx, int ky, int kz, double k2) {
+    const int64_t N = c->ppd;
+    double sep    = c->boxsize / N;
+    double nyq    = M_PI / sep;
+    double k2cut  = nyq * nyq / (c->k_cutoff * c->k_cutoff);
+    double ikcut  = 1.0 / c->k_cutoff;
+    int kmax      = (int) ((double) (N / 2) * ikcut + .5);
+    return (abs(kx) == kmax || abs(kz) == kmax || abs(ky) == kmax) || (!c->corner_modes && k2 >= k2cut)
+           || (c->qonemode && !(kx == c->one_mode[0] && ky == c->one_mode[1] && kz == c->one_mode[2]));
+}
+
+/* cgauss<2> (src/power_spectrum.cpp:338-359) from the mode's two raw draws and P(k) */
+static void zo_cgauss(const zo_config *c, double P, uint64_t r1, uint64_t r2, zo_mode *m) {
+    double R = zo_one_rand(r1);
+    double t = zo_one_rand(r2);
+    if (!c->fixed_power)
+        R = sqrt(-P * log(R));
+    else
+        R = sqrt(P);
+    t     = 2 * M_PI * t;
+    m->Dr = R * cos(t);
+    m->Di = R * sin(t);
+}
+
+/* eigenmode + growth + rescale (src/zeldovich.cpp:404-434) of a mode whose density D is already in m */
+static void zo_finish_mode(const zo_state *st, int kx, int ky, int kz, double k2, zo_mode *m) {
+    const zo_config *c = &st->c;
+    double fund = 2.0 * M_PI / c->boxsize;
+    double ik2  = 1. / k2;
+    double e[4];
+    zo_get_eig(st, kx, ky, kz, c->ppd, e);
+    double rescale = 1., f = 1.0;
+    if (c->qPLT) {
+        f = (sqrt(1. + 24 * e[3] * c->f_cluster) - 1) * .25;
+        if (c->qPLTrescale) {
+            double target_f = (sqrt(1. + 24 * c->f_cluster) - 1) / 4.;
+            double a_NL     = 1. / (1 + c->PLT_target_z);
+            double a0       = 1. / (1 + c->z_initial);
+            rescale         = pow(a_NL / a0, target_f - f);
+        }
+    }
+    for (int d = 0; d < 3; d++) m->s[d] = rescale * e[d] * fund * ik2;
+    m->f = f;
+}
+
 /* The primary mode at signed integer wavevector (kx,ky,kz), ky in [0, ppd/2):
  * mask (src/zeldovich.cpp:350-358), RNG position (SURVEY.md A.2 = the nskip
  * bookkeeping of :335,341,358-363), cgauss<2> (src/power_spectrum.cpp:338-359),
@@ -418,28 +464,15 @@ static void zo_primary(const zo_state *st, u128 seed_state, int kx, int ky, int 
     memset(m, 0, sizeof(*m));
     double fund   = 2.0 * M_PI / c->boxsize;
     double fund2  = fund * fund;
-    double sep    = c->boxsize / N;
-    double nyq    = M_PI / sep;
-    double k2cut  = nyq * nyq / (c->k_cutoff * c->k_cutoff);
-    double ikcut  = 1.0 / c->k_cutoff;
-    int kmax      = (int) ((double) (N / 2) * ikcut + .5);
     double k2     = (kx * kx + ky * ky + kz * kz) * fund2;
     double kmag   = sqrt(k2);
-    int masked = (abs(kx) == kmax || abs(kz) == kmax || abs(ky) == kmax) || (!c->corner_modes && k2 >= k2cut)
-                 || (c->qonemode && !(kx == c->one_mode[0] && ky == c->one_mode[1] && kz == c->one_mode[2]));
-    if (!masked) {
+    if (!zo_masked(c, kx, ky, kz, k2)) {
         u128 off = 2 * ((u128) ky * M * M + (u128) (kz < 0 ? kz + M : kz) * M + (u128) (kx < 0 ? kx + M : kx));
         u128 s   = zo_jump(seed_state, off);
         double P = zo_power(st, kmag);
-        double R = zo_one_rand(zo_next(&s));
-        double t = zo_one_rand(zo_next(&s));
-        if (!c->fixed_power)
-            R = sqrt(-P * log(R));
-        else
-            R = sqrt(P);
-        t     = 2 * M_PI * t;
-        m->Dr = R * cos(t);
-        m->Di = R * sin(t);
+        uint64_t r1 = zo_next(&s);
+        uint64_t r2 = zo_next(&s);
+        zo_cgauss(c, P, r1, r2, m);
     }
     if (k2 == 0.0) k2 = 1.0;
     if (c->f_NL != 0.) {
@@ -459,44 +492,12 @@ static void zo_primary(const zo_state *st, u128 seed_state, int kx, int ky, int 
     }
     if (m->Dr == 0.0 && m->Di == 0.0) return; /* "D != 0." guard, src/zeldovich.cpp:403 */
     if (c->f_NL != 0. && !st->phi) return;     /* phi-generation pass: only D and M are used (:388-394) */
-
-    double ik2 = 1. / k2;
-    double e[4];
-    zo_get_eig(st, kx, ky, kz, N, e);
-    double rescale = 1., f = 1.0;
-    if (c->qPLT) {
-        f = (sqrt(1. + 24 * e[3] * c->f_cluster) - 1) * .25;
-        if (c->qPLTrescale) {
-            double target_f = (sqrt(1. + 24 * c->f_cluster) - 1) / 4.;
-            double a_NL     = 1. / (1 + c->PLT_target_z);
-            double a0       = 1. / (1 + c->z_initial);
-            rescale         = pow(a_NL / a0, target_f - f);
-        }
-    }
-    for (int d = 0; d < 3; d++) m->s[d] = rescale * e[d] * fund * ik2;
-    m->f = f;
+    zo_finish_mode(st, kx, ky, kz, k2, m);
 }
 
-/* The four packed arrays' entries at lattice site (x,y,z) of the spectral cube
- * (SURVEY.md A.6; src/zeldovich.cpp:447-466 packing, :485-503 ky=0 plane,
- * src/block_array.cpp:487-491 + src/zeldovich.cpp:644-650 y-shift and Nyquist row). */
-static void zo_site(const zo_state *st, u128 seed_state, int64_t x, int64_t y, int64_t z, double out[8]) {
-    const int64_t N = st->c.ppd;
-    for (int i = 0; i < 8; i++) out[i] = 0.0;
-    if (y == N / 2) return;
-    if (x == 0 && y == 0 && z == 0) return;
-    int kx = zo_wrap(x, N), ky = zo_wrap(y, N), kz = zo_wrap(z, N);
-    int conj = (ky < 0) || (ky == 0 && (z > N / 2 || (z == 0 && x > N / 2)));
-    zo_mode m;
-    if (conj) {
-        /* the entry is the conjugate-structured twin of the primary mode at -k,
-         * where -k is formed on lattice INDICES (N-i, 0->0) and then wrapped, so an
-         * index of N/2 stays +N/2 */
-        kx = zo_wrap((N - x) % N, N);
-        ky = zo_wrap((N - y) % N, N);
-        kz = zo_wrap((N - z) % N, N);
-    }
-    zo_primary(st, seed_state, kx, ky, kz, &m);
+/* packed entries A0..A3 of a mode, primary or conjugate-structured twin form (src/zeldovich.cpp:447-466) */
+static void zo_pack(const zo_mode *mp, int conj, double out[8]) {
+    const zo_mode m = *mp;
     /* F = i s0 D etc. */
     double Fr = -m.s[0] * m.Di, Fi = m.s[0] * m.Dr;
     double Gr = -m.s[1] * m.Di, Gi = m.s[1] * m.Dr;
@@ -521,6 +522,29 @@ static void zo_site(const zo_state *st, u128 seed_state, int64_t x, int64_t y, i
         out[6] = Gr * f + Hi * f;
         out[7] = -(Gi * f) + Hr * f;
     }
+}
+
+/* The four packed arrays' entries at lattice site (x,y,z) of the spectral cube
+ * (SURVEY.md A.6; src/zeldovich.cpp:447-466 packing, :485-503 ky=0 plane,
+ * src/block_array.cpp:487-491 + src/zeldovich.cpp:644-650 y-shift and Nyquist row). */
+static void zo_site(const zo_state *st, u128 seed_state, int64_t x, int64_t y, int64_t z, double out[8]) {
+    const int64_t N = st->c.ppd;
+    for (int i = 0; i < 8; i++) out[i] = 0.0;
+    if (y == N / 2) return;
+    if (x == 0 && y == 0 && z == 0) return;
+    int kx = zo_wrap(x, N), ky = zo_wrap(y, N), kz = zo_wrap(z, N);
+    int conj = (ky < 0) || (ky == 0 && (z > N / 2 || (z == 0 && x > N / 2)));
+    zo_mode m;
+    if (conj) {
+        /* the entry is the conjugate-structured twin of the primary mode at -k,
+         * where -k is formed on lattice INDICES (N-i, 0->0) and then wrapped, so an
+         * index of N/2 stays +N/2 */
+        kx = zo_wrap((N - x) % N, N);
+        ky = zo_wrap((N - y) % N, N);
+        kz = zo_wrap((N - z) % N, N);
+    }
+    zo_primary(st, seed_state, kx, ky, kz, &m);
+    zo_pack(&m, conj, out);
 }
 
 /* ------------------------------------------------------------ FFT ---------- */
@@ -660,6 +684,29 @@ size_t zo_record_bytes(int icformat) {
     return 0;
 }
 
+/* one particle record (src/output.cpp:128-156; layouts include/output.h:19-42), padding bytes zeroed */
+static void zo_write_record(int icformat, unsigned char *r, size_t rb, int64_t z, int64_t y, int64_t x, const double pos[3],
+                            const double vel[3]) {
+    memset(r, 0, rb);
+    uint16_t ijk[3] = {(uint16_t) z, (uint16_t) y, (uint16_t) x};
+    if (icformat == 0) {
+        memcpy(r, ijk, 6);
+        double d[3] = {pos[2], pos[1], pos[0]};
+        memcpy(r + 8, d, 24);
+    } else if (icformat == 1) {
+        memcpy(r, ijk, 6);
+        float d[6] = {(float) pos[2], (float) pos[1], (float) pos[0], (float) vel[2], (float) vel[1], (float) vel[0]};
+        memcpy(r + 8, d, 24);
+    } else if (icformat == 2) {
+        memcpy(r, ijk, 6);
+        double d[6] = {pos[2], pos[1], pos[0], vel[2], vel[1], vel[0]};
+        memcpy(r + 8, d, 48);
+    } else {
+        float d[3] = {(float) pos[2], (float) pos[1], (float) pos[0]};
+        memcpy(r, d, 12);
+    }
+}
+
 /* WriteParticlesSlab (src/output.cpp:41-234) for all z: records in [z][y][x] order
  * with padding bytes zeroed; stats = {sum dens^2, max_disp[0..2]} where max_disp
  * keeps the SIGNED value of the largest |pos[j]| seen in (z,y,x) scan order. */
@@ -686,25 +733,7 @@ void zo_emit(const zo_config *cfg, const double *cube, unsigned char *records, d
                     vel[1] = pos[1] * vnorm;
                     vel[2] = pos[2] * vnorm;
                 }
-                unsigned char *r = records + rb * (size_t) ((z * N + y) * N + x);
-                memset(r, 0, rb);
-                uint16_t ijk[3] = {(uint16_t) z, (uint16_t) y, (uint16_t) x};
-                if (cfg->icformat == 0) {
-                    memcpy(r, ijk, 6);
-                    double d[3] = {pos[2], pos[1], pos[0]};
-                    memcpy(r + 8, d, 24);
-                } else if (cfg->icformat == 1) {
-                    memcpy(r, ijk, 6);
-                    float d[6] = {(float) pos[2], (float) pos[1], (float) pos[0], (float) vel[2], (float) vel[1], (float) vel[0]};
-                    memcpy(r + 8, d, 24);
-                } else if (cfg->icformat == 2) {
-                    memcpy(r, ijk, 6);
-                    double d[6] = {pos[2], pos[1], pos[0], vel[2], vel[1], vel[0]};
-                    memcpy(r + 8, d, 48);
-                } else {
-                    float d[3] = {(float) pos[2], (float) pos[1], (float) pos[0]};
-                    memcpy(r, d, 12);
-                }
+                zo_write_record(cfg->icformat, records + rb * (size_t) ((z * N + y) * N + x), rb, z, y, x, pos, vel);
                 for (int j = 0; j < 3; j++)
                     if (fabs(pos[j]) > fabs(md[j])) md[j] = pos[j];
                 var += dens * dens;
@@ -727,5 +756,157 @@ int zo_run(const zo_config *cfg, int nrows, const double *ks, const double *ps, 
     for (int a = 0; a < na; a++) zo_fft3_backward(cube + 2 * a * N * N * N, N);
     zo_emit(cfg, cube, records, stats);
     free(cube);
+    return 0;
+}
+
+/* ------------------------------------------------------------ selected planes at any size ----
+ * Records of nplanes chosen z planes without ever holding the cube: the z transform of those planes is summed
+ * directly, A(x,y,z0) = sum_z' S(x,y,z') exp(2 pi i z' z0 / N) with S the spectral entries of zo_site, then the
+ * plane goes through the 2-D transform and the record writer of zo_emit.  O(N^3) mode evaluations (each primary
+ * mode is evaluated once and feeds its own site and its twin's), O(nplanes narray N^2) memory — PPD=1024 and
+ * 2048 fit any host, which is what lets the benchmark configurations face the oracle.
+ *
+ * Same arithmetic as zo_run per mode (zo_masked / zo_cgauss / zo_finish_mode / zo_pack); what differs is
+ * book-keeping only: P(k) is tabulated per integer |k|^2 with the very expression zo_primary evaluates, and the
+ * generator walks a row of consecutive kx sequentially (consecutive kx are consecutive draw pairs, masked sites
+ * consume theirs: the reference's nskip walk, src/zeldovich.cpp:335,341,358-363) instead of jumping per mode.
+ * tests/test_oracle.py pins it to zo_run.  No f_NL (the potential pass needs the whole cube).
+ * records: [nplanes][N][N] records; stats: [nplanes][4] = sum dens^2, max_disp[3] of each plane. */
+int zo_planes(const zo_config *cfg, int nrows, const double *ks, const double *ps, int64_t eig_ppd, const double *eig, int nplanes,
+              const int64_t *zs, unsigned char *records, double *stats) {
+    const int64_t N = cfg->ppd, M = 65536, half = N / 2;
+    const int na = zo_narray(cfg);
+    if ((N & (N - 1)) || cfg->f_NL != 0. || nplanes < 1 || nplanes > 16) return 1;
+    for (int p = 0; p < nplanes; p++)
+        if (zs[p] < 0 || zs[p] >= N) return 1;
+    zo_state st;
+    zo_init_state(&st, cfg, nrows, ks, ps, eig_ppd, eig);
+    const u128 s0 = zo_seed_state((uint64_t) (int64_t) cfg->seed);
+    const double fund = 2.0 * M_PI / cfg->boxsize, fund2 = fund * fund;
+    const int64_t nm = 3 * half * half + 1;
+    double *ptab = (double *) malloc(sizeof(double) * nm);
+    double *tw   = (double *) malloc(sizeof(double) * 2 * N);
+    /* accumulators [y][x][p][a] while summing (one mode touches one contiguous run), [p][a][y][x] for the 2-D transform */
+    double *acc0 = (double *) calloc((size_t) nplanes * na * N * N * 2, sizeof(double));
+    double *acc  = (double *) malloc((size_t) nplanes * na * N * N * 2 * sizeof(double));
+    if (!ptab || !tw || !acc || !acc0) return 2;
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < nm; m++) ptab[m] = zo_power(&st, sqrt((double) m * fund2));
+    for (int64_t j = 0; j < N; j++) {
+        long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double) j / (long double) N;
+        tw[2 * j]       = (double) cosl(ang);
+        tw[2 * j + 1]   = (double) sinl(ang);
+    }
+#define ZO_ACC(p, a, y, x) (acc0 + 2 * ((((size_t) (y) * N + (x)) * nplanes + (p)) * na + (a)))
+    /* the ky = 0 plane (its own twin, src/zeldovich.cpp:485-503): plain zo_site per entry */
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t x = 0; x < N; x++)
+        for (int64_t z = 0; z < N; z++) {
+            double v[8];
+            zo_site(&st, s0, x, 0, z, v);
+            for (int p = 0; p < nplanes; p++) {
+                const int64_t j = (z * zs[p]) % N;
+                const double wr = tw[2 * j], wi = tw[2 * j + 1];
+                for (int a = 0; a < na; a++) {
+                    double *o = ZO_ACC(p, a, 0, x);
+                    o[0] += v[2 * a] * wr - v[2 * a + 1] * wi;
+                    o[1] += v[2 * a] * wi + v[2 * a + 1] * wr;
+                }
+            }
+        }
+    /* primary rows ky = 1 .. N/2-1 and their twins at y = N - ky; the row y = N/2 stays zero */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t ky = 1; ky < half; ky++)
+        for (int64_t z = 0; z < N; z++) {
+            const int kz = zo_wrap(z, N);
+            /* whole row masked?  The plane tests do not involve kx and the sphere cut grows with kx^2, so the row is
+             * masked as soon as its kx = 0 site is (not with ZD_qonemode, whose test involves kx) */
+            if (!cfg->qonemode && zo_masked(cfg, 0, (int) ky, kz, (double) (ky * ky + (int64_t) kz * kz) * fund2)) continue;
+            const u128 rowoff = 2 * ((u128) ky * M * M + (u128) (kz < 0 ? kz + M : kz) * M);
+            u128 s = zo_jump(s0, rowoff);
+            const int64_t zt = (N - z) % N; /* the twin's plane */
+            double pw[16][2], pwt[16][2];
+            for (int p = 0; p < nplanes; p++) {
+                int64_t j = (z * zs[p]) % N, jt = (zt * zs[p]) % N;
+                pw[p][0] = tw[2 * j], pw[p][1] = tw[2 * j + 1];
+                pwt[p][0] = tw[2 * jt], pwt[p][1] = tw[2 * jt + 1];
+            }
+            for (int64_t x = 0; x < N; x++) {
+                const int kx = zo_wrap(x, N);
+                if (x == half + 1) s = zo_jump(s0, rowoff + 2 * (u128) (kx + M)); /* kx = -N/2+1: position (kx mod 65536) */
+                const uint64_t r1 = zo_next(&s), r2 = zo_next(&s);
+                const int64_t n2 = (int64_t) kx * kx + ky * ky + (int64_t) kz * kz;
+                double k2 = (kx * kx + (int) ky * (int) ky + kz * kz) * fund2;
+                if (zo_masked(cfg, kx, (int) ky, kz, k2)) continue;
+                zo_mode m;
+                memset(&m, 0, sizeof(m));
+                zo_cgauss(cfg, ptab[n2], r1, r2, &m);
+                if (m.Dr == 0.0 && m.Di == 0.0) continue;
+                zo_finish_mode(&st, kx, (int) ky, kz, k2, &m);
+                double v[8], vt[8];
+                zo_pack(&m, 0, v);
+                zo_pack(&m, 1, vt);
+                const int64_t xt = (N - x) % N, yt = N - ky;
+                for (int p = 0; p < nplanes; p++)
+                    for (int a = 0; a < na; a++) {
+                        double *o = ZO_ACC(p, a, ky, x);
+                        o[0] += v[2 * a] * pw[p][0] - v[2 * a + 1] * pw[p][1];
+                        o[1] += v[2 * a] * pw[p][1] + v[2 * a + 1] * pw[p][0];
+                        double *t = ZO_ACC(p, a, yt, xt);
+                        t[0] += vt[2 * a] * pwt[p][0] - vt[2 * a + 1] * pwt[p][1];
+                        t[1] += vt[2 * a] * pwt[p][1] + vt[2 * a + 1] * pwt[p][0];
+                    }
+            }
+        }
+#pragma omp parallel for schedule(static)
+    for (int64_t y = 0; y < N; y++)
+        for (int64_t x = 0; x < N; x++)
+            for (int p = 0; p < nplanes; p++)
+                for (int a = 0; a < na; a++) {
+                    const double *src = ZO_ACC(p, a, y, x);
+                    double *dst       = acc + 2 * ((((size_t) p * na + a) * N + y) * N + x);
+                    dst[0] = src[0], dst[1] = src[1];
+                }
+    free(acc0);
+#undef ZO_ACC
+#define ZO_ACC(p, a, y, x) (acc + 2 * ((((size_t) (p) * na + (a)) * N + (y)) * N + (x)))
+    /* 2-D backward transform of every accumulated plane */
+#pragma omp parallel
+    {
+        double *tmp = (double *) malloc(sizeof(double) * 2 * N);
+#pragma omp for collapse(2)
+        for (int64_t q = 0; q < (int64_t) nplanes * na; q++)
+            for (int64_t y = 0; y < N; y++) zo_fft1(acc + 2 * ((size_t) q * N * N + y * N), N, 1, tw, tmp);
+#pragma omp for collapse(2)
+        for (int64_t q = 0; q < (int64_t) nplanes * na; q++)
+            for (int64_t x = 0; x < N; x++) zo_fft1(acc + 2 * ((size_t) q * N * N + x), N, N, tw, tmp);
+        free(tmp);
+    }
+    /* WriteParticlesSlab for the chosen planes (src/output.cpp:41-234), as zo_emit */
+    const size_t rb = zo_record_bytes(cfg->icformat);
+    const double vnorm = cfg->qPLT ? 1.0 : (sqrt(1. + 24 * cfg->f_cluster) - 1) * .25;
+    for (int p = 0; p < nplanes; p++) {
+        double var = 0.0, md[3] = {0, 0, 0};
+        for (int64_t y = 0; y < N; y++)
+            for (int64_t x = 0; x < N; x++) {
+                const double *a0 = ZO_ACC(p, 0, y, x), *a1 = ZO_ACC(p, 1, y, x);
+                double dens = a0[0];
+                double pos[3] = {a0[1], a1[0], a1[1]}, vel[3];
+                if (na == 4) {
+                    const double *a2 = ZO_ACC(p, 2, y, x), *a3 = ZO_ACC(p, 3, y, x);
+                    vel[0] = a2[1] * vnorm, vel[1] = a3[0] * vnorm, vel[2] = a3[1] * vnorm;
+                } else {
+                    vel[0] = pos[0] * vnorm, vel[1] = pos[1] * vnorm, vel[2] = pos[2] * vnorm;
+                }
+                zo_write_record(cfg->icformat, records + rb * ((size_t) p * N * N + (size_t) (y * N + x)), rb, zs[p], y, x, pos, vel);
+                for (int j = 0; j < 3; j++)
+                    if (fabs(pos[j]) > fabs(md[j])) md[j] = pos[j];
+                var += dens * dens;
+            }
+        stats[4 * p] = var, stats[4 * p + 1] = md[0], stats[4 * p + 2] = md[1], stats[4 * p + 3] = md[2];
+    }
+#undef ZO_ACC
+    free(ptab), free(tw), free(acc);
+    if (st.have_spline) zo_spline_free(&st.sp);
     return 0;
 }

@@ -95,6 +95,8 @@ def lib():
         L.zo_emit.argtypes = [C.POINTER(Config), dp, C.c_void_p, dp]
         L.zo_run.argtypes = [C.POINTER(Config), C.c_int, dp, dp, C.c_int64, dp, C.c_void_p, dp]
         L.zo_run.restype = C.c_int
+        L.zo_planes.argtypes = [C.POINTER(Config), C.c_int, dp, dp, C.c_int64, dp, C.c_int, C.POINTER(C.c_int64), C.c_void_p, dp]
+        L.zo_planes.restype = C.c_int
         L.zo_record_bytes.argtypes = [C.c_int]
         L.zo_record_bytes.restype = C.c_size_t
         L.zo_narray.argtypes = [C.POINTER(Config)]
@@ -184,6 +186,23 @@ def run(cfg, pk, eig=None):
     if rc:
         raise RuntimeError(f"zo_run failed rc={rc}")
     return rec, dict(density_variance=stats[0], max_disp=stats[1:4].copy())
+
+
+def planes(cfg, pk, zs, eig=None):
+    """Records of the chosen z planes at any size (zo_planes: direct z summation, no cube).
+    Returns (records [len(zs), N, N], list of per-plane stats dicts)."""
+    n, k, p = _table(pk)
+    pe, tab = _eig(eig)
+    N = cfg.ppd
+    zs = np.ascontiguousarray(zs, dtype=np.int64)
+    dt = RECORD_DTYPES[cfg.icformat]
+    rec = np.zeros((len(zs), N, N), dtype=dt)
+    stats = np.zeros((len(zs), 4))
+    rc = lib().zo_planes(C.byref(cfg), n, _dp(k), _dp(p), pe, _dp(tab), len(zs), zs.ctypes.data_as(C.POINTER(C.c_int64)),
+                         rec.ctypes.data_as(C.c_void_p), _dp(stats))
+    if rc:
+        raise RuntimeError(f"zo_planes failed rc={rc}")
+    return rec, [dict(density_variance=s[0], max_disp=s[1:4].copy()) for s in stats]
 
 
 # ---------------------------------------------------------------- reference binary

@@ -26,6 +26,17 @@ def pkg():
     return load_package()
 
 
+def ctx_from(pkg, P, power, rank=0, nranks=1):
+    """Another context (e.g. another slab rank) from already parsed parameters and an already normalised spectrum."""
+    cfg = P.config(device=0)
+    cfg.rank, cfg.nranks = rank, nranks
+    ctx = pkg.Context(cfg)
+    power.apply(ctx)
+    if P.qPLT:
+        ctx.load_eigenmodes_file(P.PLT_filename)
+    return ctx
+
+
 def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
     """Product context from keyword parameters; the spline comes from the product's own host code."""
     synth = load_synth()
@@ -137,13 +148,26 @@ def test_host_scalars_match_oracle(pkg, oracle):
 # ---------------------------------------------------------------- FFT ---------------
 @pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048])
 @pytest.mark.parametrize("row_mode", [True, False])
-def test_fft_matches_numpy(pkg, n, row_mode):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fft_matches_numpy(pkg, n, row_mode, variant):
+    """variant 0: the kernels a default context launches (TMA-ring strided passes where they exist); 1: the plain kernels."""
     rng = np.random.RandomState(n)
     batch = 64
     shape = (batch, n) if row_mode else (n, batch)
     a = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
-    got = pkg.fft_backward(a, row_mode)
+    got = pkg.fft_backward(a, row_mode, variant)
     want = np.fft.ifft(a, axis=1 if row_mode else 0) * n  # unnormalised backward, sign +1
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-14
+
+
+@pytest.mark.parametrize("batch", [64, 8 * 37])
+def test_fft2048_decimation_kernel_matches_numpy(pkg, batch):
+    """The 8-pencil decimation-in-time kernel for the N = 2048 strided passes (csrc/zplt_fft2048_kernels.cu)."""
+    n = 2048
+    rng = np.random.RandomState(batch)
+    a = rng.standard_normal((n, batch)) + 1j * rng.standard_normal((n, batch))
+    got = pkg.fft_backward(a, False, 2)
+    want = np.fft.ifft(a, axis=0) * n
     assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-14
 
 
@@ -183,6 +207,131 @@ def test_spectral_arrays_before_fft(pkg, oracle, case):
     assert np.max(np.abs(got - want)) / scale < 1e-13
     # masked sites are exactly zero in both
     assert np.array_equal(got == 0, want == 0)
+    ctx.close()
+
+
+# ---------------------------------------------------------------- the hot kernel ----
+@pytest.mark.parametrize("case", [
+    dict(ppd=32),
+    dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, f_cluster=0.97, icformat="RVdoubleZel", eig=16),
+    dict(ppd=128, qPLT=1, icformat="RVZel", eig=128),
+    dict(ppd=256, k_cutoff=2.0, seed=-3),
+    dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128),
+    dict(ppd=64, f_NL=3000.0, n_s=0.96, Omega_M=0.3),
+])
+def test_hot_generation_kernel_before_fft(pkg, oracle, case):
+    """The packed arrays as gen_xfft_kernel — the product's generation kernel — forms them (its x transform skipped):
+    run walk of the generator, eigenmode cell sharing, zero-row skip, pencil builder, twin rows, ky = 0 plane."""
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    got = ctx.spectral_hot()
+    want = oracle.spectral_cube(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got - want)) / scale < 1e-13
+    assert np.array_equal(got == 0, want == 0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("ppd,kc,na4", [(64, 1.0, 0), (256, 1.0, 0), (128, 2.0, 0), (512, 1.0, 1)])
+def test_hot_generation_kernel_draws_bit_exact(pkg, oracle, ppd, kc, na4):
+    """The raw 64-bit draws gen_xfft_kernel consumes, site by site, against the reference's sequential walk of the plane
+    generators (oracle.pcg_draws at the closed-form position): bit-exact, in the kernel that ships.  512 with 4 arrays
+    is the 8-pencil / runs-of-2 instantiation."""
+    synth = load_synth()
+    eig = (16, synth.make_eigmodes(16)) if na4 else None
+    kw = default_kw(ppd=ppd, k_cutoff=kc, qPLT=na4, icformat="RVZel")
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    raw = ctx.hot_draws()  # [z][y][x][2]
+    ctx.close()
+    N, h = ppd, ppd // 2
+    k1 = np.where(np.arange(N) > h, np.arange(N) - N, np.arange(N))
+    kmax = int(h / kc + 0.5)
+    fund2 = (2 * np.pi / 720.0) ** 2
+    k2cut = (np.pi / (720.0 / N)) ** 2 / (kc * kc)
+    rng = np.random.RandomState(ppd)
+    rows = [(0, 0), (0, h), (1, N - 1), (h - 1, h + 1), (3, 5)] + [(int(rng.randint(0, h)), int(rng.randint(0, N))) for _ in range(40)]
+    checked = 0
+    for y, z in rows:
+        if y == 0 and z > h:
+            # these entries are the twins of row (0, N - z) (reference src/zeldovich.cpp:485-503 overwrites what it drew here)
+            assert not raw[z, y].any()
+            continue
+        kz = int(k1[z])
+        n2 = k1.astype(np.int64) ** 2 + y * y + kz * kz
+        masked = (np.abs(k1) == kmax) | (abs(kz) == kmax) | (y == kmax) | (n2 * fund2 >= k2cut)
+        if masked.all():
+            assert not raw[z, y].any()  # the kernel skips all-masked rows without drawing
+            continue
+        # the reference's walk of this row: kx = 0..N/2 are consecutive draw pairs, then kx = -N/2+1..-1 at (kx mod 65536)
+        base = 2 * (y * M * M + (kz % M) * M)
+        want = np.empty((N, 2), dtype=np.uint64)
+        want[:h + 1] = oracle.pcg_draws(12346, base, 2 * (h + 1)).reshape(-1, 2)
+        want[h + 1:] = oracle.pcg_draws(12346, base + 2 * (M - h + 1), 2 * (h - 1)).reshape(-1, 2)
+        # every site of a run that holds an unmasked site consumes its draws; runs are 16/NP sites (2, 4 or 8) — compare the unmasked ones
+        assert np.array_equal(raw[z, y][~masked], want[~masked]), (y, z)
+        checked += int((~masked).sum())
+    assert checked > 1000
+
+
+# ---------------------------------------------------------------- benchmark sizes ---
+_PLANES = {}
+
+
+def oracle_planes(oracle, kw, zs, eig):
+    """oracle.planes, remembered per configuration (the large sizes cost the CPU a minute)."""
+    key = (tuple(sorted((k, str(v)) for k, v in kw.items())), tuple(zs), eig[0] if eig else None)
+    if key not in _PLANES:
+        _PLANES.clear()  # one entry: the records of four PPD=2048 planes are 0.5 GB
+        _PLANES[key] = oracle.planes(oracle.make_config(**kw), helpers.wmap_pk(), zs, eig)
+    return _PLANES[key]
+
+
+def plane_check(pkg, oracle, ctx, kw, eig, zs, zlocal0=0, tol64=TOL):
+    """Selected planes of a generated context against the plane oracle (direct z summation, oracle.planes)."""
+    want, wst = oracle_planes(oracle, kw, zs, eig)
+    worst = 0.0
+    for i, z in enumerate(zs):
+        ctx.reset_stats()
+        got = ctx.fetch_planes(z - zlocal0, 1)
+        worst = max(worst, compare_records(oracle, got, want[i].reshape(-1), tol64=tol64))
+        st = ctx.stats()
+        assert abs(st["density_variance"] / wst[i]["density_variance"] - 1) < 1e-9
+        assert np.allclose(st["max_disp"], wst[i]["max_disp"], rtol=1e-9)
+    return worst
+
+
+@pytest.mark.parametrize("case", [
+    # BASELINE configs[3] exactly — the bench.py workload: PPD=1024 qPLT + rescale, RVZel
+    dict(ppd=1024, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128),
+    # the same arrays through the double-precision records (configs[1]'s format)
+    dict(ppd=1024, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=128),
+    # PPD=512 qPLT: the 8-pencil / runs-of-2 generation kernel, ring kernels at N=512
+    dict(ppd=512, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128),
+    # configs[2]'s large run: PPD=512 with ZD_k_cutoff=2, ZA
+    dict(ppd=512, k_cutoff=2.0, icformat="RVdoubleZel"),
+])
+def test_benchmark_configs_vs_plane_oracle(pkg, oracle, case):
+    """The benchmark configurations against the CPU oracle: planes 0, 1, N/2-1 and N-1 of the full-size runs.
+    ids exact; float32 fields to one ulp of the field scale (2e-7), double fields to 1e-10."""
+    import torch
+
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    N = kw["ppd"]
+    need = (4 if kw["qPLT"] else 2) * 16 * N**3 + (8 << 30)
+    if torch.cuda.mem_get_info()[0] < need:
+        pytest.skip("not enough free device memory")
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    ctx.generate()
+    worst = plane_check(pkg, oracle, ctx, kw, eig, [0, 1, N // 2 - 1, N - 1])
+    print(case, "worst field-relative error", worst)
     ctx.close()
 
 
@@ -347,6 +496,115 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     assert np.allclose(md, wst["max_disp"], rtol=1e-10)
 
 
+@pytest.mark.parametrize("G,opts,case", [
+    (2, {}, dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16)),
+    (4, {}, dict(ppd=64, icformat="RVZel")),
+    (8, {}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    (8, {"slab_ring": 0, "yring": 0, "slab_groups": 3}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    (2, {"slab_groups": 1, "p2p_ctas": 0}, dict(ppd=128, k_cutoff=2.0, icformat="Zeldovich")),
+    (4, {}, dict(ppd=512, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+])
+def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
+    """The product's multi-GPU stage 1 on one GPU: every rank of a G-rank run executes the grouped, overlapped generation
+    and fft_tile_p2p(_ring)_kernel — the z pass that stores straight into the owners' receive buffers — with the other
+    ranks' buffers on the same device standing in for NVLink peers (zplt_dbg_set_peers).  Records vs the oracle."""
+    import torch
+
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    N = kw["ppd"]
+    ctx0, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig, rank=0, nranks=G)
+    ctxs = [ctx0] + [ctx_from(pkg, P, power, r, G) for r in range(1, G)]
+    bufs = [torch.empty(c.workspace_bytes() // 8, dtype=torch.float64, device="cuda:0") for c in ctxs]
+    half_bytes = ctxs[0].workspace_bytes() // 2
+    for c, b in zip(ctxs, bufs):
+        for k, v in opts.items():
+            c.set_option(k, v)
+        c.set_workspace(b.data_ptr(), b.numel() * 8)
+        b.fill_(float("nan"))  # every row of every receive buffer must be written by somebody
+    for c in ctxs:
+        c.dbg_set_peers([b.data_ptr() + half_bytes for b in bufs])
+    for c in ctxs:
+        c.generate()
+    for c in ctxs:
+        c.synchronize()
+    torch.cuda.synchronize()
+    parts, var, md = [], 0.0, np.zeros(3)
+    for c in ctxs:
+        c.exchange_done()
+        parts.append(c.fetch_planes(0, N // G))
+        st = c.stats()
+        var += st["density_variance"]
+        md = np.where(np.abs(st["max_disp"]) > np.abs(md), st["max_disp"], md)
+    got = np.concatenate(parts)
+    if N <= 256:
+        want, wst = oracle.run(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+        compare_records(oracle, got, want)
+        assert abs(var / wst["density_variance"] - 1) < 1e-10
+        assert np.allclose(md, wst["max_disp"], rtol=1e-10)
+    else:
+        zs = [0, N // G - 1, N // G, N // 2 + 1, N - 1]
+        want, _ = oracle_planes(oracle, kw, zs, eig)
+        g3 = got.reshape(N, N * N)
+        for i, z in enumerate(zs):
+            compare_records(oracle, g3[z], want[i].reshape(-1))
+    for c in ctxs:
+        c.close()
+    del bufs
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dit", [0, 1])
+def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit):
+    """BASELINE configs[4] (the north-star size): PPD=2048 qPLT + rescale RVZel over 8 slab ranks.  One GPU cannot hold
+    the run, but it can hold ONE rank's buffers: the 8 ranks run their stage 1 one after the other in the same workspace,
+    each storing only the share of the rank under test (the other peers are NULL = discarded), which then runs its
+    stage 2.  Every N = 2048 kernel of the product (generation, z pass + exchange — 4-pencil and 8-pencil decimation
+    forms —, y pass + emission) faces the oracle: planes 0 and 255 of rank 0, 1792 and 2047 of rank 7."""
+    import torch
+
+    N, G = 2048, 8
+    kw = default_kw(ppd=N, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel")
+    synth = load_synth()
+    eig = (128, synth.make_eigmodes(128))
+    ctx0, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig, rank=0, nranks=G)
+    ws = ctx0.workspace_bytes()
+    if torch.cuda.mem_get_info()[0] < ws + (6 << 30):
+        ctx0.close()
+        pytest.skip("needs ~145 GB of free device memory")
+    W = torch.empty(ws // 8, dtype=torch.float64, device="cuda:0")
+    recv = W.data_ptr() + ws // 2
+    zs = [0, N // G - 1, N - N // G, N - 1]
+    want, _ = oracle_planes(oracle, kw, zs, eig)
+    ctx0.close()
+    worst = 0.0
+    for target, planes in ((0, (0, 1)), (G - 1, (2, 3))):
+        W[ws // 16:].fill_(float("nan"))
+        tctx = None
+        for src in range(G):
+            c = ctx_from(pkg, P, power, src, G)
+            c.set_option("dit2048", dit)
+            c.set_workspace(W.data_ptr(), ws)
+            c.dbg_set_peers([recv if r == target else None for r in range(G)])
+            c.generate()
+            c.synchronize()
+            if src == target:
+                tctx = c
+            else:
+                c.close()
+        tctx.exchange_done()
+        for i in planes:
+            got = tctx.fetch_planes(zs[i] - target * (N // G), 1)
+            worst = max(worst, compare_records(oracle, got, want[i].reshape(-1)))
+        tctx.close()
+    del W
+    torch.cuda.empty_cache()
+    print("PPD=2048 qPLT+rescale RVZel, 8 ranks, dit2048 =", dit, ": worst field-relative error", worst)
+
+
 # ---------------------------------------------------------------- option coverage ---
 @pytest.mark.parametrize("case", [
     dict(ppd=32, qonemode=1, one_mode=(3, 2, -5)),
@@ -481,29 +739,20 @@ def test_kernel_variants_agree_at_full_size(pkg):
     kw = default_kw(ppd=1024, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel")
     ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
     planes = (0, 1, 511, 1023)
-    switches = ("ZPLT_ZRING", "ZPLT_YRING", "ZPLT_WIDE_RECORDS")
+    defaults = {"zring": 12, "yring": 12, "wide_records": -1}
 
-    def run(env):
-        saved = {k: os.environ.get(k) for k in switches}
-        for k in switches:
-            os.environ.pop(k, None)
-        os.environ.update(env)
-        try:
-            ctx.generate()
-            return [ctx.fetch_planes(z, 1).copy() for z in planes]
-        finally:
-            for k, v in saved.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
+    def run(opts):
+        for k, v in {**defaults, **opts}.items():
+            ctx.set_option(k, v)
+        ctx.generate()
+        return [ctx.fetch_planes(z, 1).copy() for z in planes]
 
-    ref = run({"ZPLT_ZRING": "0", "ZPLT_YRING": "0", "ZPLT_WIDE_RECORDS": "0"})
-    for env in ({}, {"ZPLT_WIDE_RECORDS": "0"}, {"ZPLT_YRING": "0"}, {"ZPLT_ZRING": "0"}):
-        got = run(dict(env))
+    ref = run({"zring": 0, "yring": 0, "wide_records": 0})
+    for opts in ({}, {"wide_records": 0}, {"yring": 0}, {"zring": 0}):
+        got = run(opts)
         for a, b in zip(got, ref):
-            assert np.array_equal(a["ijk"], b["ijk"]) and np.all(a["pad"] == 0), env
+            assert np.array_equal(a["ijk"], b["ijk"]) and np.all(a["pad"] == 0), opts
             for f in ("displ", "vel"):
                 scale = float(np.abs(b[f]).max())
-                assert float(np.abs(a[f].astype(np.float64) - b[f].astype(np.float64)).max()) <= 2e-7 * scale, (env, f)
+                assert float(np.abs(a[f].astype(np.float64) - b[f].astype(np.float64)).max()) <= 2e-7 * scale, (opts, f)
     ctx.close()

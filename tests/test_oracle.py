@@ -86,6 +86,44 @@ def test_oracle_oversampling_identity(oracle):
         assert oracle.field_rel_err(b["displ"][:, c], a["displ"][:, c]) < 1e-13
 
 
+@pytest.mark.parametrize("case", [
+    dict(ppd=64, icformat="RVZel"),
+    dict(ppd=32, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, f_cluster=0.97, icformat="RVdoubleZel", eig=16),
+    dict(ppd=32, qPLT=1, icformat="RVZel", eig=64, seed=-5),
+    dict(ppd=32, k_cutoff=2.0, corner_modes=1, icformat="Zeldovich"),
+    dict(ppd=16, qonemode=1, one_mode=(-3, 2, 5), icformat="ZelSimple"),
+    dict(ppd=32, k_cutoff=2.0, fixed_power=1, icformat="RVdoubleZel"),
+])
+def test_plane_oracle_matches_full_oracle(oracle, case):
+    """zo_planes (selected planes by direct z summation — what faces the benchmark sizes) against zo_run, itself pinned to
+    the reference-generated goldens above: ids and float32 casts identical, double fields to 1e-13."""
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    synth = helpers.load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    cfg = oracle.make_config(**case)
+    N = cfg.ppd
+    full, _ = oracle.run(cfg, helpers.wmap_pk(), eig)
+    full = full.reshape(N, N, N)
+    zs = [0, 1, N // 2 - 1, N // 2, N - 1]
+    rec, st = oracle.planes(cfg, helpers.wmap_pk(), zs, eig)
+    for i, z in enumerate(zs):
+        want = full[z]
+        if "ijk" in want.dtype.names:
+            assert np.array_equal(rec[i]["ijk"], want["ijk"]) and np.all(rec[i]["pad"] == 0)
+        for f in ("displ", "vel"):
+            if f in want.dtype.names:
+                tol = 2e-7 if want[f].dtype == np.float32 else 1e-13
+                for c in range(3):
+                    # scale of the whole field, not of the plane
+                    err = np.max(np.abs(rec[i][f][..., c].astype(np.float64) - want[f][..., c])) / np.max(np.abs(full[f][..., c]))
+                    assert err < tol, (z, f, c, err)
+        if want.dtype.names[0] == "ijk" and "displ" in want.dtype.names:
+            md = st[i]["max_disp"]  # (pos0, pos1, pos2) = (displ[2], displ[1], displ[0])
+            for j in range(3):
+                assert abs(abs(md[j]) - np.max(np.abs(want["displ"][..., 2 - j]))) <= 2e-7 * abs(md[j])
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(helpers.ROOT, "oracle", "_ref", "zeldovich_ref")), reason="reference binary not built")
 def test_oracle_matches_live_reference(oracle):
     synth = helpers.load_synth()

@@ -93,7 +93,8 @@ EXPORTS = [
     "zplt_set_power_law", "zplt_set_primordial", "zplt_set_eigenmodes", "zplt_workspace_bytes", "zplt_set_workspace", "zplt_set_stream",
     "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_emit_planes_density", "zplt_fetch_planes_density",
     "zplt_write_outputs", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
-    "zplt_get_timings", "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
+    "zplt_get_timings", "zplt_set_option", "zplt_dbg_set_peers", "zplt_dbg_spectral_hot", "zplt_dbg_hot_draws", "zplt_dbg_fft_variant",
+    "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_ipc_close", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
     "zplt_power_sigmaR", "zplt_power_infer_Tk", "zplt_power_primordial_norm", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
@@ -140,6 +141,7 @@ def lib():
     L.zplt_exchange_done.argtypes = [vp]
     L.zplt_ipc_export.argtypes = [vp, C.c_char_p]
     L.zplt_ipc_import.argtypes = [vp, i32, C.c_char_p]
+    L.zplt_ipc_close.argtypes = [vp]
     L.zplt_slab_owner.argtypes = [i64, i32, i64, C.POINTER(i32), C.POINTER(i32)]
     L.zplt_slab_offset.argtypes = [i64, i32, i32, i32, i32, i32, i64, i64]
     L.zplt_slab_offset.restype = i64
@@ -149,6 +151,11 @@ def lib():
     L.zplt_dbg_spectral.argtypes = [vp, dp]
     L.zplt_dbg_after_generate.argtypes = [vp, dp]
     L.zplt_dbg_fft.argtypes = [i32, i64, i32, dp]
+    L.zplt_dbg_fft_variant.argtypes = [i32, i64, i32, i32, dp]
+    L.zplt_dbg_spectral_hot.argtypes = [vp, dp]
+    L.zplt_dbg_hot_draws.argtypes = [vp, C.POINTER(u64)]
+    L.zplt_dbg_set_peers.argtypes = [vp, i32, C.POINTER(vp)]
+    L.zplt_set_option.argtypes = [vp, C.c_char_p, i32]
     L.zplt_params_load.argtypes = [C.c_char_p, C.POINTER(Params)]
     L.zplt_icformat_code.argtypes = [C.c_char_p]
     L.zplt_config_from_params.argtypes = [C.POINTER(Params), C.POINTER(Config)]
@@ -250,8 +257,10 @@ class PowerSpectrum:
 
 def make_config(ppd, boxsize=720.0, seed=12346, k_cutoff=1.0, corner_modes=0, qonemode=0, one_mode=(0, 0, 0), qPLT=0,
                 qPLTrescale=0, PLT_target_z=0.0, z_initial=49.0, f_cluster=1.0, fixed_power=0, icformat="RVZel", device=-1,
-                rank=0, nranks=1, **_ignored):
+                rank=0, nranks=1, f_NL=0.0, n_s=1.0, Omega_M=1.0):
+    """``zplt_config`` from keywords; unknown keywords raise (nothing is silently dropped)."""
     c = Config()
+    c.f_NL, c.n_s, c.Omega_M = f_NL, n_s, Omega_M
     c.ppd, c.boxsize, c.seed, c.k_cutoff = ppd, boxsize, seed, k_cutoff
     c.corner_modes, c.qonemode = corner_modes, qonemode
     c.one_mode[:] = list(one_mode)
@@ -364,6 +373,9 @@ class Context:
         assert len(blob) == 64 * len(handles)
         _ck(lib().zplt_ipc_import(self._h, len(handles), blob))
 
+    def ipc_close(self):
+        _ck(lib().zplt_ipc_close(self._h))
+
     def exchange_done(self):
         _ck(lib().zplt_exchange_done(self._h))
 
@@ -380,9 +392,19 @@ class Context:
         _ck(lib().zplt_synchronize(self._h))
 
     def timings(self):
+        """Device milliseconds of the last generate / emit calls: generation + x FFT (one kernel), z FFT, y FFT + emission."""
         t = np.zeros(8)
         _ck(lib().zplt_get_timings(self._h, _dp(t)))
-        return dict(generate_ms=t[0], zfft_ms=t[1], yfft_ms=t[2], xfft_emit_ms=t[3], launches=[int(v) for v in t[4:8]])
+        return dict(gen_xfft_ms=t[0], zfft_ms=t[1], yfft_emit_ms=t[3], launches=[int(v) for v in t[4:8]])
+
+    def set_option(self, name, value):
+        """Tuning / diagnostic switch (struct Tuning, csrc/zplt_internal.h)."""
+        _ck(lib().zplt_set_option(self._h, name.encode(), int(value)))
+
+    def dbg_set_peers(self, recv_ptrs):
+        """Same-device stand-ins for the peers' receive buffers (None = discard that rank's share)."""
+        arr = (C.c_void_p * len(recv_ptrs))(*[C.c_void_p(p) if p else C.c_void_p(None) for p in recv_ptrs])
+        _ck(lib().zplt_dbg_set_peers(self._h, len(recv_ptrs), arr))
 
     def write_ic_files(self, output_dir, cpd):
         _ck(lib().zplt_write_ic_files(self._h, os.fsencode(output_dir), cpd))
@@ -405,6 +427,20 @@ class Context:
         N = self.ppd
         out = np.zeros((self.narray, N, N, N), dtype=np.complex128)
         _ck(lib().zplt_dbg_spectral(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def spectral_hot(self):
+        """The packed arrays as the HOT generation kernel forms them (its transform skipped)."""
+        N = self.ppd
+        out = np.zeros((self.narray, N, N, N), dtype=np.complex128)
+        _ck(lib().zplt_dbg_spectral_hot(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def hot_draws(self):
+        """Raw 64-bit draws consumed by the hot generation kernel: uint64 [z][y < ppd/2][x][2] (skipped rows stay 0)."""
+        N = self.ppd
+        out = np.zeros((N, N // 2, N, 2), dtype=np.uint64)
+        _ck(lib().zplt_dbg_hot_draws(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
 
     def after_generate(self):
@@ -431,14 +467,15 @@ def pcg_draws(seed, offset, n):
     return out
 
 
-def fft_backward(data, row_mode=True):
-    """Unnormalised backward FFT along the last (row_mode) or first axis of a 2-D complex array, on the GPU."""
+def fft_backward(data, row_mode=True, variant=0):
+    """Unnormalised backward FFT along the last (row_mode) or first axis of a 2-D complex array, on the GPU.
+    variant 0: the kernels a default context uses; 1: plain one-tile-per-CTA kernels; 2: 8-pencil decimation (n = 2048)."""
     a = np.ascontiguousarray(data, dtype=np.complex128).copy()
     if row_mode:
         batch, n = a.shape
     else:
         n, batch = a.shape
-    _ck(lib().zplt_dbg_fft(n, batch, 1 if row_mode else 0, a.ctypes.data_as(C.POINTER(C.c_double))))
+    _ck(lib().zplt_dbg_fft_variant(n, batch, 1 if row_mode else 0, variant, a.ctypes.data_as(C.POINTER(C.c_double))))
     return a
 
 

@@ -77,6 +77,7 @@ struct zplt_ctx {
     size_t slab_elems;  // complex elements of one slab buffer
     bool exchanged;
     bool p2p;               // peers' stage-2 buffers are mapped: the z pass stores straight into them
+    bool dbg_peers;         // ... through zplt_dbg_set_peers (same-device buffers, tests) rather than CUDA IPC
     cplx *peer_recv[16];
     void *peer_base[16];    // what cudaIpcOpenMemHandle returned (to close)
     double vnorm;
@@ -90,6 +91,8 @@ struct zplt_ctx {
     double *ptab;
     long long ptab_count;
     double *spx, *spy, *spy2;
+    int sp_n;          // nodes the spline arrays were allocated for
+    size_t eig_bytes;  // bytes the eigenmode table was allocated for
     u128 *ystate;
     Affine *zjump, *xjump;
     double *eig;
@@ -111,7 +114,42 @@ struct zplt_ctx {
     cudaEvent_t ev_emit[2 * ZPLT_MAX_EMIT_EVENTS];
     int n_emit_ev;
     int launches[4];
+    Tuning tn;     // switches: environment defaults read once in zplt_create, zplt_set_option afterwards
+    LaunchRes lr;  // work counters of the persistent kernels, SM count
 };
+
+// ZPLT_<NAME> environment defaults of the tuning switches, read once per context
+static void tuning_from_env(Tuning &t) {
+    struct {
+        const char *name;
+        int *v;
+    } tab[] = {{"ZPLT_ZRING", &t.zring},           {"ZPLT_YRING", &t.yring},           {"ZPLT_WIDE_RECORDS", &t.wide_records},
+               {"ZPLT_EMIT_SCRATCH", &t.emit_scratch}, {"ZPLT_EMIT_PREFETCH", &t.emit_prefetch}, {"ZPLT_SLAB_GROUPS", &t.slab_groups},
+               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_SLAB_RING", &t.slab_ring},
+               {"ZPLT_GEN_PERSIST", &t.gen_persist}};
+    for (auto &e : tab) {
+        const char *s = getenv(e.name);
+        if (s && *s) *e.v = atoi(s);
+    }
+}
+
+extern "C" int zplt_set_option(zplt_ctx *c, const char *name, int32_t value) {
+    if (!c || !name) return fail(ZPLT_EINVAL, "null argument");
+    Tuning &t = c->tn;
+    struct {
+        const char *name;
+        int *v;
+    } tab[] = {{"zring", &t.zring},           {"yring", &t.yring},           {"wide_records", &t.wide_records},
+               {"emit_scratch", &t.emit_scratch}, {"emit_prefetch", &t.emit_prefetch}, {"slab_groups", &t.slab_groups},
+               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"slab_ring", &t.slab_ring},
+               {"gen_persist", &t.gen_persist}};
+    for (auto &e : tab)
+        if (!strcmp(e.name, name)) {
+            *e.v = value;
+            return ZPLT_OK;
+        }
+    return fail(ZPLT_EINVAL, "unknown option \"%s\"", name);
+}
 
 extern "C" const char *zplt_last_error(void) { return g_err.c_str(); }
 
@@ -153,6 +191,7 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     const long long N = cfg->ppd;
     if (N < 16 || N > 2048 || (N & (N - 1)))
         return fail(ZPLT_EINVAL, "ppd=%lld unsupported: this build handles power-of-two ppd in [16, 2048]", N);
+    if (cfg->nranks > 16) return fail(ZPLT_EINVAL, "nranks=%d unsupported: at most 16 ranks (one node)", cfg->nranks);
     if (!(cfg->boxsize > 0)) return fail(ZPLT_EINVAL, "BoxSize must be positive");
     if (!(cfg->k_cutoff >= 1)) return fail(ZPLT_EINVAL, "ZD_k_cutoff must be >= 1");
     if (!(cfg->f_cluster > 0. && cfg->f_cluster <= 1.)) return fail(ZPLT_EINVAL, "ZD_f_cluster must be in (0,1]");
@@ -183,6 +222,11 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     c->N      = (int) N;
     c->na     = cfg->qPLT ? 4 : 2;
     c->device = dev;
+    c->tn     = Tuning();
+    tuning_from_env(c->tn);
+    c->lr     = LaunchRes();
+    c->lr.sms = prop.multiProcessorCount;
+    CK(cudaMalloc((void **) &c->lr.counters, 64 * sizeof(unsigned int)));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {
@@ -302,6 +346,7 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     cudaFree(c->scratch);
     cudaFree(c->phi);
     cudaFree(c->mtab);
+    cudaFree(c->lr.counters);
     for (int i = 0; i < 2; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
         if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -332,13 +377,25 @@ extern "C" int zplt_set_power_spline(zplt_ctx *c, int32_t n, const double *x, co
                                      double normalization, double Pk_smooth2) {
     if (!c || !x || !y || !y2 || n < 2) return fail(ZPLT_EINVAL, "bad spline arguments");
     CK(cudaSetDevice(c->device));
-    cudaFree(c->spx), cudaFree(c->spy), cudaFree(c->spy2);
-    c->spx = c->spy = c->spy2 = nullptr;
-    int rc;
-    if ((rc = upload((void **) &c->spx, x, n * sizeof(double), c->stream))) return rc;
-    if ((rc = upload((void **) &c->spy, y, n * sizeof(double), c->stream))) return rc;
-    if ((rc = upload((void **) &c->spy2, y2, n * sizeof(double), c->stream))) return rc;
-    return build_power_table(c, 0, 0.0, n, normalization, Pk_smooth2);
+    // the tables are re-uploaded in place when their size has not changed: no cudaFree/cudaMalloc (both synchronise the
+    // device) on a context that is fed new inputs every step; the copies are ordered on the context's stream
+    if (c->sp_n != n) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->spx), cudaFree(c->spy), cudaFree(c->spy2);
+        c->spx = c->spy = c->spy2 = nullptr;
+        c->sp_n = 0;
+        CK(cudaMalloc((void **) &c->spx, n * sizeof(double)));
+        CK(cudaMalloc((void **) &c->spy, n * sizeof(double)));
+        CK(cudaMalloc((void **) &c->spy2, n * sizeof(double)));
+        c->sp_n = n;
+    }
+    CK(cudaMemcpyAsync(c->spx, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->spy, y, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->spy2, y2, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    int rc = build_power_table(c, 0, 0.0, n, normalization, Pk_smooth2);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));  // the host arrays are the caller's: they may change after this returns
+    return ZPLT_OK;
 }
 
 extern "C" int zplt_set_power_law(zplt_ctx *c, double index, double normalization, double Pk_smooth2) {
@@ -358,11 +415,17 @@ extern "C" int zplt_set_primordial(zplt_ctx *c, double primordial_norm) {
 extern "C" int zplt_set_eigenmodes(zplt_ctx *c, int32_t ppd_e, const double *table) {
     if (!c || !table || ppd_e < 2 || (ppd_e & 1)) return fail(ZPLT_EINVAL, "bad eigenmode table");
     CK(cudaSetDevice(c->device));
-    cudaFree(c->eig);
-    c->eig       = nullptr;
     size_t bytes = (size_t) ppd_e * ppd_e * (ppd_e / 2 + 1) * 4 * sizeof(double);
-    int rc;
-    if ((rc = upload((void **) &c->eig, table, bytes, c->stream))) return rc;
+    if (c->eig_bytes != bytes) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->eig);
+        c->eig       = nullptr;
+        c->eig_bytes = 0;
+        CK(cudaMalloc((void **) &c->eig, bytes));
+        c->eig_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(c->eig, table, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // the host table is the caller's
     c->gp.eig        = c->eig;
     c->gp.pe         = ppd_e;
     c->gp.eig_direct = (ppd_e % c->N == 0);
@@ -378,9 +441,15 @@ extern "C" int zplt_set_workspace(zplt_ctx *c, void *p, size_t bytes) {
     if (!c || !p) return fail(ZPLT_EINVAL, "null argument");
     if (bytes < c->cube_bytes) return fail(ZPLT_EINVAL, "workspace too small: %zu < %zu", bytes, c->cube_bytes);
     if (((uintptr_t) p) & 255) return fail(ZPLT_EINVAL, "workspace must be 256-byte aligned");
+    if (c->p2p && !c->dbg_peers)
+        return fail(ZPLT_ESTATE, "the workspace is mapped by the peers (zplt_ipc_export); it cannot be replaced");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));  // nothing queued may still use the old buffer
+    CK(cudaStreamSynchronize(c->xchg_stream));
     if (c->own_cube && c->cube) cudaFree(c->cube);
-    c->cube     = (cplx *) p;
-    c->own_cube = false;
+    c->cube      = (cplx *) p;
+    c->own_cube  = false;
+    c->generated = false;
     return ZPLT_OK;
 }
 
@@ -437,7 +506,7 @@ static int run_potential(zplt_ctx *c) {
     const int T = fft_tile_T(N);
     const int axes[3] = {0, 2, 1};
     for (int pass = 0; pass < 2; pass++) {
-        for (int i = 0; i < 3; i++) CK(launch_fft_tiles_any(N, T, c->phi, geom_axis(N, 1, axes[i]), c->tw, c->stream));
+        for (int i = 0; i < 3; i++) CK(launch_fft_tiles_any(N, T, c->phi, geom_axis(N, 1, axes[i]), c->tw, c->tn, c->lr, c->stream));
         if (pass == 0) CK(launch_fnl_local(c->phi, N, c->cfg.f_NL, c->stream));
     }
     c->gp.phi  = c->phi;
@@ -467,7 +536,9 @@ static TileGeom geom_axis(int N, int na, int axis) {
     return g;
 }
 
-static int run_generate(zplt_ctx *c, bool with_fft) {
+// with_fft = false: the packed spectral arrays without any transform (introspection).  hot = true forms them with the
+// fused generation kernel itself (its transform skipped), otherwise with the plain one-thread-per-mode kernel.
+static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
     int rc = ready(c);
     if (rc) return rc;
     c->launches[0] = c->launches[1] = c->launches[2] = c->launches[3] = 0;
@@ -478,13 +549,12 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
         if ((rc = run_potential(c))) return rc;
         c->launches[0] += 10;
     }
-    const int gt = with_fft ? gen_xfft_T(c->N, c->na) : 0;
+    const int gt = (with_fft || hot) ? gen_xfft_T(c->N, c->na) : 0;
     if (slab && c->p2p) {
         // Slab rank with mapped peers: stage 1 runs in groups of rows.  The z pass of group j (NVLink-bound,
         // on the high-priority exchange stream) overlaps with the generation + x pass of group j+1.
         if (!gt) return fail(ZPLT_EINVAL, "no fused generation kernel for this size");
-        int J = 8;  // measured on 2 GPUs at PPD=1024: 1 group 69.4 ms/step, 4 groups 61.6, 8 groups + 96 CTAs 57.4
-        if (const char *e = getenv("ZPLT_SLAB_GROUPS")) J = atoi(e);
+        int J = c->tn.slab_groups;  // measured on 2 GPUs at PPD=1024: 1 group 69.4 ms/step, 4 groups 61.6, 8 groups + 96 CTAs 57.4
         if (J < 1) J = 1;
         if (J > 16) J = 16;
         while (J > 1 && (c->sg.h % J)) J--;
@@ -492,10 +562,10 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
         sg.nly      = c->sg.h / J;
         for (int j = 0; j < J; j++) {
             sg.ly0 = j * sg.nly;
-            CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->stream));
+            CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->tn, c->lr, false, c->stream));
             CK(cudaEventRecord(c->ev_group[j], c->stream));
             CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[j], 0));
-            CK(launch_fft_tiles_p2p_any(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, c->xchg_stream));
+            CK(launch_fft_tiles_p2p_any(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, c->tn, c->lr, c->xchg_stream));
         }
         c->launches[0] = J;
         c->launches[1] = J;
@@ -503,33 +573,28 @@ static int run_generate(zplt_ctx *c, bool with_fft) {
         CK(cudaEventRecord(c->ev_join, c->xchg_stream));
         CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     } else {
-    if (gt) {
-        // fused: draw the modes and transform the x axis in one kernel
-        CK(launch_gen_xfft(c->N, gt, c->gp, c->sg, c->cube, c->tw, c->stream));
-        c->launches[0] += 1;
-    } else {
-        if (slab) return fail(ZPLT_EINVAL, "no fused generation kernel for this size");
-        CK(launch_generate(c->gp, c->cube, c->stream));
-        c->launches[0] += 1;
-        if (with_fft) {
-            CK(launch_fft_tiles_any(c->N, fft_tile_T(c->N), c->cube, geom_axis(c->N, c->na, 0), c->tw, c->stream));
+        if (gt) {
+            // fused: draw the modes and transform the x axis in one kernel
+            CK(launch_gen_xfft(c->N, gt, c->gp, c->sg, c->cube, c->tw, c->tn, c->lr, !with_fft, c->stream));
+            c->launches[0] += 1;
+        } else {
+            CK(launch_generate(c->gp, c->cube, c->stream));
             c->launches[0] += 1;
         }
-    }
-    CK(cudaEventRecord(c->ev_gen[1], c->stream));
-    if (with_fft) {
-        TileGeom g = geom_axis(c->N, c->na, 2);
-        if (slab) {
-            // stage-1 buffer B1[z][a][slot][x]: pencils along z for each of the na*2h local rows
-            const int T = fft_tile_T(c->N);
-            g.astride = 0, g.grid_z = 1;
-            g.ostride = c->N, g.grid_y = c->na * 2 * c->sg.h;
-            g.tstride = T, g.grid_x = c->N / T, g.pa = T, g.plo_stride = 1, g.phi_stride = 0;
-            g.nstride = (long long) c->na * 2 * c->sg.h * c->N;
+        CK(cudaEventRecord(c->ev_gen[1], c->stream));
+        if (with_fft) {
+            TileGeom g = geom_axis(c->N, c->na, 2);
+            if (slab) {
+                // stage-1 buffer B1[z][a][slot][x]: pencils along z for each of the na*2h local rows
+                const int T = fft_tile_T(c->N);
+                g.astride = 0, g.grid_z = 1;
+                g.ostride = c->N, g.grid_y = c->na * 2 * c->sg.h;
+                g.tstride = T, g.grid_x = c->N / T, g.pa = T, g.plo_stride = 1, g.phi_stride = 0;
+                g.nstride = (long long) c->na * 2 * c->sg.h * c->N;
+            }
+            CK(launch_fft_tiles_any(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->tn, c->lr, c->stream));
+            c->launches[1] = 1;
         }
-        CK(launch_fft_tiles_any(c->N, fft_tile_T(c->N), c->cube, g, c->tw, c->stream));
-        c->launches[1] = 1;
-    }
     }
     CK(cudaEventRecord(c->ev_gen[2], c->stream));
     // the y axis is transformed inside the emission kernel (zplt_emit_planes)
@@ -563,20 +628,21 @@ extern "C" int zplt_emit_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, voi
     ep.out          = (unsigned char *) device_out;
     ep.dens         = device_density;
     ep.stats        = c->stats;
-    ep.scratch      = (getenv("ZPLT_EMIT_SCRATCH") && atoi(getenv("ZPLT_EMIT_SCRATCH")) == 0) ? nullptr : c->scratch;
-    {
-        // 256-bit record stores: default = on in the ring emission kernel (ZPLT_WIDE_RECORDS=0 forces the two 16-byte halves)
-        const char *e = getenv("ZPLT_WIDE_RECORDS");
-        ep.wide_records = e ? atoi(e) : -1;
-    }
-    {
-        const char *e = getenv("ZPLT_EMIT_PREFETCH");
-        ep.prefetch = e ? atoi(e) : 1;
+    ep.scratch      = c->tn.emit_scratch ? c->scratch : nullptr;
+    ep.wide_records = c->tn.wide_records;  // 256-bit record stores: default (-1) = on in the ring emission kernel
+    ep.prefetch     = c->tn.emit_prefetch;
+    const long long N2 = (long long) c->N * c->N;
+    if (c->sg.G == 1) {  // the cube [a][z][y][x]
+        ep.astride = N2 * c->N, ep.zstride = N2, ep.zglobal0 = 0, ep.nzl = c->N;
+    } else if (c->p2p) {  // after the fused exchange: [zl][a][y][x], rows at their true y
+        ep.astride = N2, ep.zstride = N2 * c->na, ep.zglobal0 = (long long) c->sg.rank * nplanes, ep.nzl = nplanes;
+    } else {  // after a caller-run all-to-all: per-source blocks B2[src][zl][a][slot][x] (zplt_slab.h)
+        ep.astride = 0, ep.zstride = 0, ep.zglobal0 = (long long) c->sg.rank * nplanes, ep.nzl = nplanes;
     }
     bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
     if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
     CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->sg.G > 1 ? c->cube + c->slab_elems : c->cube, c->sg, z0, nz, ep, c->tw,
-                               c->stream, &c->launches[3]));
+                               c->tn, c->lr, c->stream, &c->launches[3]));
     if (timed) {
         CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev + 1], c->stream));
         c->n_emit_ev++;
@@ -634,6 +700,7 @@ extern "C" int zplt_fetch_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, vo
 extern "C" int zplt_exchange_info(zplt_ctx *c, void **send, void **recv, size_t *bytes_per_peer) {
     if (!c) return fail(ZPLT_EINVAL, "null context");
     if (c->sg.G == 1) return fail(ZPLT_EINVAL, "a single-GPU context has no exchange");
+    if (c->p2p) return fail(ZPLT_ESTATE, "the exchange is fused into zplt_generate (peers are mapped); there are no blocks to move");
     int rc = ensure_cube(c);
     if (rc) return rc;
     if (send) *send = c->cube;
@@ -674,6 +741,36 @@ extern "C" int zplt_ipc_import(zplt_ctx *c, int32_t nranks, const void *handles)
         c->peer_recv[r] = (cplx *) base + c->slab_elems;
     }
     c->p2p = true;
+    return ZPLT_OK;
+}
+
+extern "C" int zplt_ipc_close(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->xchg_stream));
+    for (int r = 0; r < 16; r++) {
+        if (c->peer_base[r]) CK(cudaIpcCloseMemHandle(c->peer_base[r]));
+        c->peer_base[r] = nullptr;
+        c->peer_recv[r] = nullptr;
+    }
+    c->p2p = c->dbg_peers = false;
+    c->generated = false;
+    return ZPLT_OK;
+}
+
+// Test hook: stage-2 buffers on the SAME device stand in for the peers (one GPU runs fft_tile_p2p_kernel and the grouped,
+// overlapped stage 1 of every rank of a slab run).  recv[r] = where rank r's stage-2 buffer is, or NULL to discard that
+// rank's share (a single rank of a run whose other ranks' buffers would not fit), this context's own included.
+extern "C" int zplt_dbg_set_peers(zplt_ctx *c, int32_t nranks, void *const *recv) {
+    if (!c || !recv) return fail(ZPLT_EINVAL, "null argument");
+    if (nranks != c->sg.G || nranks > 16 || nranks < 2) return fail(ZPLT_EINVAL, "expected %d receive buffers", c->sg.G);
+    if (c->p2p && !c->dbg_peers) return fail(ZPLT_ESTATE, "peers are already mapped through CUDA IPC");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_cube(c);
+    if (rc) return rc;
+    for (int r = 0; r < nranks; r++) c->peer_recv[r] = (cplx *) recv[r];
+    c->p2p = c->dbg_peers = true;
     return ZPLT_OK;
 }
 
@@ -818,13 +915,33 @@ extern "C" int zplt_dbg_power_table(zplt_ctx *c, int64_t count, double *host_out
     return ZPLT_OK;
 }
 
-extern "C" int zplt_dbg_spectral(zplt_ctx *c, double *host_out) {
+static int dbg_spectral(zplt_ctx *c, double *host_out, bool hot) {
     if (!host_out) return fail(ZPLT_EINVAL, "null argument");
-    int rc = run_generate(c, false);
+    int rc = run_generate(c, false, hot);
     if (rc) return rc;
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(host_out, c->cube, c->cube_bytes, cudaMemcpyDeviceToHost));
     return ZPLT_OK;
+}
+extern "C" int zplt_dbg_spectral(zplt_ctx *c, double *host_out) { return dbg_spectral(c, host_out, false); }
+extern "C" int zplt_dbg_spectral_hot(zplt_ctx *c, double *host_out) { return dbg_spectral(c, host_out, true); }
+
+extern "C" int zplt_dbg_hot_draws(zplt_ctx *c, uint64_t *host_raw) {
+    if (!c || !host_raw) return fail(ZPLT_EINVAL, "null argument");
+    if (c->sg.G > 1) return fail(ZPLT_EINVAL, "single-GPU introspection only");
+    if (c->cfg.f_NL != 0.) return fail(ZPLT_EINVAL, "with ZD_f_NL the hot kernel reads the potential instead of drawing");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t) c->N * (c->N / 2) * c->N * 2 * sizeof(uint64_t);
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **) &d, bytes));
+    CK(cudaMemsetAsync(d, 0, bytes, c->stream));
+    c->gp.dbg_raw = d;
+    int rc        = run_generate(c, false, true);
+    c->gp.dbg_raw = nullptr;
+    if (rc == ZPLT_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(ZPLT_ECUDA, "generation kernel failed");
+    if (rc == ZPLT_OK && cudaMemcpy(host_raw, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(ZPLT_ECUDA, "copy failed");
+    cudaFree(d);
+    return rc;
 }
 
 extern "C" int zplt_dbg_after_generate(zplt_ctx *c, double *host_out) {
@@ -838,7 +955,17 @@ extern "C" int zplt_dbg_after_generate(zplt_ctx *c, double *host_out) {
 }
 
 extern "C" int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *host_data) {
+    return zplt_dbg_fft_variant(n, batch, row_mode, 0, host_data);
+}
+
+// variant 0: the kernels a default context uses (ring-prefetched where they exist); 1: the plain one-tile-per-CTA kernels;
+// 2: the 8-pencil decimation kernel (n = 2048, strided pencils)
+extern "C" int zplt_dbg_fft_variant(int32_t n, int64_t batch, int32_t row_mode, int32_t variant, double *host_data) {
     if (!host_data) return fail(ZPLT_EINVAL, "null argument");
+    Tuning tn;
+    LaunchRes lr;
+    if (variant == 1) tn.zring = 0;
+    if (variant == 2) tn.dit2048 = 1;
     const int T = fft_tile_T(n);
     if (T == 0) return fail(ZPLT_EINVAL, "unsupported FFT length %d", n);
     if (batch <= 0 || batch % T) return fail(ZPLT_EINVAL, "batch must be a positive multiple of %d for n=%d", T, n);
@@ -861,10 +988,16 @@ extern "C" int zplt_dbg_fft(int32_t n, int64_t batch, int32_t row_mode, double *
     } else {
         g.nstride = batch, g.plo_stride = 1, g.tstride = T;
     }
-    CK(launch_fft_tiles_any(n, T, d, g, dtw, 0));
+    {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&lr.sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaMalloc((void **) &lr.counters, 64 * sizeof(unsigned int)));
+    }
+    CK(launch_fft_tiles_any(n, T, d, g, dtw, tn, lr, 0));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_data, d, bytes, cudaMemcpyDeviceToHost));
-    cudaFree(d), cudaFree(dtw);
+    cudaFree(d), cudaFree(dtw), cudaFree(lr.counters);
     return ZPLT_OK;
 }
 

@@ -89,6 +89,9 @@ struct GenParams {
     // the reference takes.  mtab[m] = M(k = sqrt(m) * fundamental), the potential -> density factor.
     const double2 *phi;
     const double *mtab;
+    // introspection of the hot kernel (parity tests): when non-NULL, primary_run stores the two raw 64-bit draws of every
+    // site it walks at dbg_raw[((z*N/2 + y)*N + x)*2 ..] (rows it skips as all-masked stay untouched)
+    unsigned long long *dbg_raw;
 };
 
 struct Mode {
@@ -327,8 +330,13 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
 #pragma unroll
         for (int j = 0; j < RUN; j++) {
             if (j == 1 && x0 == half) s = apply(g.xjump[x0 + 1], rc.s_yz);
-            u1[j] = u64_to_unit(pcg_next(s));
-            u2[j] = u64_to_unit(pcg_next(s));
+            const uint64_t r1 = pcg_next(s), r2 = pcg_next(s);
+            u1[j] = u64_to_unit(r1);
+            u2[j] = u64_to_unit(r2);
+            if (g.dbg_raw != nullptr) {
+                unsigned long long *o = g.dbg_raw + (((size_t) (kz < 0 ? kz + N : kz) * half + ky) * N + (x0 + j)) * 2;
+                o[0] = r1, o[1] = r2;
+            }
         }
     }
 #pragma unroll
@@ -446,29 +454,4 @@ __device__ __forceinline__ void pack_twin(const Mode &m, cplx a[4]) {
     a[3] = make_double2(Gr * f + Hi * f, -(Gi * f) + Hr * f);
 }
 
-}  // namespace zplt
-
-namespace zplt {
-// One packed array's entry (a = 0..3) from the stored mode state, primary or twin form
-// (same expressions as pack_primary / pack_twin, one component at a time).
-__device__ __forceinline__ cplx pack_one(double Dr, double Di, double s0, double s1, double s2, double f, int a, bool twin) {
-    const double Fr = -s0 * Di, Fi = s0 * Dr;
-    const double Gr = -s1 * Di, Gi = s1 * Dr;
-    const double Hr = -s2 * Di, Hi = s2 * Dr;
-    if (!twin) {
-        switch (a) {
-            case 0: return make_double2(Dr - Fi, Di + Fr);
-            case 1: return make_double2(Gr - Hi, Gi + Hr);
-            case 2: return make_double2(0. - Fi * f, 0. + Fr * f);
-            default: return make_double2(Gr * f - Hi * f, Gi * f + Hr * f);
-        }
-    } else {
-        switch (a) {
-            case 0: return make_double2(Dr + Fi, -Di + Fr);
-            case 1: return make_double2(Gr + Hi, -Gi + Hr);
-            case 2: return make_double2(0. + Fi * f, 0. + Fr * f);
-            default: return make_double2(Gr * f + Hi * f, -(Gi * f) + Hr * f);
-        }
-    }
-}
 }  // namespace zplt

@@ -135,6 +135,10 @@ struct FftPlan {
 };
 
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+template <int N>
+struct FftLog2 {
+    static constexpr int value = ilog2(N);
+};
 
 // Shared-memory image of the T pencils a CTA transforms together.  Thread index = slot*T + pencil,
 // 128-bit accesses are served per quarter-warp (8 lanes), conflict-free iff the 8 sixteen-byte

@@ -1,7 +1,4 @@
-// EXPERIMENTAL — compiled for sm_100a, NOT YET RUN ON A GPU (the round's GPU budget was spent when it was written).
-// Nothing here is reachable unless ZPLT_DIT2048=1 is set; the default paths do not touch this translation unit.
-// First check on a GPU: ZPLT_DIT2048=1 python -m pytest tests -m gpu -k "fft_matches_numpy and 2048" (zplt_dbg_fft goes
-// through launch_fft_tiles_any).  ptxas: 128 registers, no spills (8 bytes in the in-place variant).
+// 8-pencil decimation kernels for the N = 2048 strided passes (Tuning::dit2048).
 // The index arithmetic (exchange patterns, swizzle, slot permutation, combine) is checked thread by thread in numpy by
 // tools/proto_dit2048.py.
 //
@@ -19,9 +16,6 @@
 //       in place or straight into the peers' stage-2 buffers.
 // Replaces, for N = 2048, fft_tile_kernel<2048,4> / fft_tile_p2p_kernel<2048,4> (reference InverseFFT_Yonly,
 // src/zeldovich.cpp:93-114, and BlockArray::StoreBlock/LoadBlock, src/block_array.cpp:387-414, 466-504).
-#include <cstdlib>
-#include <cstring>
-
 #include "zplt_fft.cuh"
 #include "zplt_internal.h"
 
@@ -110,7 +104,7 @@ __device__ __forceinline__ int fft1024_split(cplx (&v)[16], double *S, int b, co
 }
 
 // One 8-pencil tile of 2048 points: src + base is element (z = 0) of this thread's pencil, rows are nstride apart;
-// store(z, value) receives the transformed element z of the pencil.
+// store(k, lo, hi) receives the transformed elements k (lo) and k + 1024 (hi) of the pencil, k < 1024.
 template <class Store>
 __device__ __forceinline__ void dit2048_tile(const cplx *__restrict__ src, long long base, long long nstride, double *S_pencil, cplx *park,
                                              const cplx *__restrict__ tw, int tid, int b, Store store) {
@@ -133,8 +127,7 @@ __device__ __forceinline__ void dit2048_tile(const cplx *__restrict__ src, long 
                 const int k  = bo + M * e;
                 const cplx t = cmul(v[e], __ldg(&tw[k]));  // W_2048^k O[k]
                 const cplx E = park[e * NT + tid];
-                store(k, cadd(E, t));
-                store(k + 1024, csub(E, t));
+                store(k, cadd(E, t), csub(E, t));  // elements k and k + 1024
             }
         }
     }
@@ -150,16 +143,20 @@ __global__ void __launch_bounds__(512, 1) fft2048_dit_kernel(cplx *__restrict__ 
     const long long base = tz * g.astride + ty * g.ostride + tx * g.tstride + p;
     cplx *dst            = data;
     const long long ns   = g.nstride;
-    dit2048_tile(data, base, ns, S + p * Split::PSTRIDE, park, tw, tid, b, [=](int z, cplx val) { __stcs(&dst[base + (long long) z * ns], val); });
+    dit2048_tile(data, base, ns, S + p * Split::PSTRIDE, park, tw, tid, b, [=](int k, cplx lo, cplx hi) {
+        __stcs(&dst[base + (long long) k * ns], lo);
+        __stcs(&dst[base + (long long) (k + 1024) * ns], hi);
+    });
 }
 
 struct PeerTable2 {
     cplx *recv[16];
 };
 
-// the z pass of a slab rank at N = 2048 with the exchange fused in (see fft_tile_p2p_kernel): 128-byte peer stores
+// the z pass of a slab rank at N = 2048 with the exchange fused in (see fft_tile_p2p_kernel): 128-byte peer stores into
+// the owners' stage-2 buffers B2[zl][a][y][x]; a NULL peer discards that rank's share
 __global__ void __launch_bounds__(512, 1)
-   fft2048_dit_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, PeerTable2 peers, const cplx *__restrict__ tw) {
+   fft2048_dit_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable2 peers, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_dit[];
     double *S  = reinterpret_cast<double *>(smem_dit);
     cplx *park = reinterpret_cast<cplx *>(smem_dit + Split::IMAGE_BYTES);
@@ -167,8 +164,9 @@ __global__ void __launch_bounds__(512, 1)
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     const int rows = sg.na * 2 * sg.h;  // x-rows per z plane of the stage-1 buffer
     const long long nstride = (long long) rows * N;
-    const int np  = N / sg.G;
+    const int np  = N / sg.G, lognp = 11 - sg.log2G;
     const int nsl = 2 * sg.nly;
+    const int na  = sg.na;
     const long long ntiles = (long long) XT * nsl * sg.na;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int xt = (int) (t % XT);
@@ -176,27 +174,29 @@ __global__ void __launch_bounds__(512, 1)
         const int slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
         const int row  = a * 2 * sg.h + slot;
         const int x    = xt * T + p;
+        const int y    = slab_row(N, sg.G, sg.rank, slot);
         const long long base = (long long) row * N + x;
-        const int rank = sg.rank;
-        dit2048_tile(b1, base, nstride, S + p * Split::PSTRIDE, park, tw, tid, b, [&](int z, cplx val) {
-            const int r = z / np, zl = z % np;
-            __stcs(&peers.recv[r][(((long long) rank * np + zl) * rows + row) * N + x], val);
+        const long long rowoff = ((long long) a * N + y) * N + x, zstride = (long long) na * N * N;
+        // planes k and k + 1024 have the same local index on ranks G/2 apart (N/G divides 1024 for G >= 2)
+        const int rhalf = sg.G >> 1;
+        dit2048_tile(b1, base, nstride, S + p * Split::PSTRIDE, park, tw, tid, b, [&](int k, cplx lo, cplx hi) {
+            const int r = k >> lognp;
+            const long long off = (long long) (k & (np - 1)) * zstride + rowoff;
+            cplx *d0 = peers.recv[r], *d1 = peers.recv[r + rhalf];
+            if (d0 != nullptr) __stcs(&d0[off], lo);
+            if (d1 != nullptr) __stcs(&d1[off], hi);
         });
     }
 }
 
-bool dit2048_enabled() {
-    const char *e = getenv("ZPLT_DIT2048");
-    return e && atoi(e) > 0;
-}
 constexpr size_t DIT_SMEM = Split::IMAGE_BYTES + Split::PARK_BYTES;
 
 }  // namespace
 
 // In-place strided pass with the N = 2048 decimation kernel when it is enabled and the geometry is the 4-pencil
 // unit-stride tiling the regular launcher would use; otherwise the regular launcher.
-int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
-    if (N == 2048 && dit2048_enabled() && g.plo_stride == 1 && g.phi_stride == 0 && g.pa == 4 && g.tstride == 4 && (g.grid_x % 2) == 0) {
+int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &g, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st) {
+    if (N == 2048 && tn.dit2048 > 0 && g.plo_stride == 1 && g.phi_stride == 0 && g.pa == 4 && g.tstride == 4 && (g.grid_x % 2) == 0) {
         TileGeom g8 = g;
         g8.pa = 8, g8.tstride = 8, g8.grid_x = g.grid_x / 2;
         cudaError_t e = cudaFuncSetAttribute(fft2048_dit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DIT_SMEM);
@@ -205,28 +205,25 @@ int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &g, const cplx
         fft2048_dit_kernel<<<(unsigned) ntiles, 512, DIT_SMEM, st>>>(data, g8, tw);
         return (int) cudaGetLastError();
     }
-    return launch_fft_tiles(N, T, data, g, tw, st);
+    return launch_fft_tiles(N, T, data, g, tw, tn, lr, st);
 }
 
-int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, cudaStream_t st) {
-    if (N == 2048 && dit2048_enabled() && sg.G <= 16) {
+int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
+                             const Tuning &tn, LaunchRes &lr, cudaStream_t st) {
+    if (N == 2048 && tn.dit2048 > 0 && sg.G <= 16) {
         cudaError_t e = cudaFuncSetAttribute(fft2048_dit_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DIT_SMEM);
         if (e != cudaSuccess) return (int) e;
         PeerTable2 pt;
         for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long ntiles = (long long) (N / 8) * 2 * sg.nly * sg.na;
-        long long nctas = sms;
-        const char *c = getenv("ZPLT_P2P_CTAS");
-        const int lim = c ? atoi(c) : 96;  // as fft_tile_p2p_kernel: leave SMs to the overlapped generation kernel
+        long long nctas = lr.sms;
+        const int lim   = tn.p2p_ctas;  // as fft_tile_p2p_kernel: leave SMs to the overlapped generation kernel
         if (lim > 0 && lim < nctas) nctas = lim;
         if (nctas > ntiles) nctas = ntiles;
         fft2048_dit_p2p_kernel<<<(unsigned) nctas, 512, DIT_SMEM, st>>>(b1, sg, pt, tw);
         return (int) cudaGetLastError();
     }
-    return launch_fft_tiles_p2p(N, T, b1, sg, peer_recv, tw, st);
+    return launch_fft_tiles_p2p(N, T, b1, sg, peer_recv, tw, tn, lr, st);
 }
 
 }  // namespace zplt

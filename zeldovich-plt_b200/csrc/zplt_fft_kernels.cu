@@ -7,7 +7,6 @@
 //                    (reference src/output.cpp:41-234): unpack Re/Im of the packed arrays
 //                    into displacement/velocity, cast to the ICFormat record, accumulate
 //                    density_variance and max_disp.
-#include <cstdlib>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 // measured in the generation kernel: table-loaded twiddles 35.4 ms vs multiplication tree 34.5 ms
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
 //   y == N/2 : the Nyquist row is zero (reference :640-650 with src/block_array.cpp:487-491)
 template <int N, int NP>
 __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
-   gen_xfft_kernel(GenParams g, SlabGeom sg, cplx *__restrict__ cube, const cplx *__restrict__ tw) {
+   gen_xfft_kernel(GenParams g, SlabGeom sg, cplx *__restrict__ cube, const cplx *__restrict__ tw, int skip_fft) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int M  = N / 16;
     constexpr int NT = NP * M;
@@ -329,7 +328,8 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
             if (origin_row && side == 0 && x == 0) val = make_double2(0.0, 0.0);
             v[e] = val;
         }
-        const int bo = fft_pencil<N, NP, false, ZPLT_GENX_TWLOAD>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);  // natural order: whole rows are stored
+        // natural order: whole rows are stored.  skip_fft (CTA-uniform): the packed arrays before the transform (introspection)
+        const int bo = skip_fft ? b : fft_pencil<N, NP, false, ZPLT_GENX_TWLOAD>(v, S + p * FftSmem<N, NP>::PSTRIDE, b, tw);
         const bool live     = (side == 0) || has_twin;
         const long long row = row_of(a, side);
         if (live) {
@@ -343,44 +343,125 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
 // z-axis pass of a slab rank with the exchange fused in: the transformed pencil is not written
 // back to the local stage-1 buffer but straight into the stage-2 buffers of the ranks that own
 // its planes — peer stores over NVLink (peer[r] is rank r's stage-2 base, opened through CUDA
-// IPC; peer[rank] is local).  This is BlockArray::StoreBlock + LoadBlock
-// (reference src/block_array.cpp:387-414, 466-504) done by the FFT epilogue, 128-byte runs.
+// IPC; peer[rank] is local; a NULL entry discards that rank's share: single-GPU tests of one rank).
+// This is BlockArray::StoreBlock + LoadBlock (reference src/block_array.cpp:387-414, 466-504) done by
+// the FFT epilogue, 128-byte runs.  The receiver's layout is free because the sender computes every
+// address: rows land at their true y, B2[zl][a][y][x], so stage 2 of a slab rank reads exactly what a
+// single GPU reads (the y shift of LoadBlock, :487-491, is the slot -> y map here).
 struct PeerTable {
     cplx *recv[16];
 };
+// tile t of a (group of a) stage-1 buffer -> x tile, packed array, slot
+__device__ __forceinline__ void p2p_tile(const SlabGeom &sg, int XT, long long t, int &xt, int &a, int &slot) {
+    const int nsl = 2 * sg.nly;
+    xt            = (int) (t % XT);
+    const int rr = (int) (t / XT), sidx = rr % nsl;
+    a    = rr / nsl;
+    slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
+}
 template <int N, int T>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
-   fft_tile_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, PeerTable peers, const cplx *__restrict__ tw) {
+   fft_tile_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable peers, const cplx *__restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *S         = reinterpret_cast<cplx *>(smem_raw);
     constexpr int M = N / 16;
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     const int rows = sg.na * 2 * sg.h;  // x-rows per z plane of the stage-1 buffer
     const long long nstride = (long long) rows * N;
-    const int np = N / sg.G;
+    const int np = N / sg.G, lognp = FftLog2<N>::value - sg.log2G;
     // persistent CTAs over the tiles (x tile, array, slot of this group): the pass is NVLink-bound, so
     // a limited number of CTAs saturates the links and leaves the other SMs to the generation
     // kernel of the next group, which runs concurrently on another stream
     constexpr int XT = N / T;
-    const int nsl    = 2 * sg.nly;
-    const long long ntiles = (long long) XT * nsl * sg.na;
+    const long long ntiles = (long long) XT * 2 * sg.nly * sg.na;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int xt = (int) (t % XT);
-        const int rr = (int) (t / XT), sidx = rr % nsl, a = rr / nsl;
-        const int slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
+        int xt, a, slot;
+        p2p_tile(sg, XT, t, xt, a, slot);
         const int row  = a * 2 * sg.h + slot;
         const int x    = xt * T + p;
+        const int y    = slab_row(N, sg.G, sg.rank, slot);
         const long long base = (long long) row * N + x;
+        const long long rowoff = ((long long) a * N + y) * N + x, zstride = (long long) sg.na * N * N;  // B2[zl][a][y][x]
         cplx v[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
         const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int z = bo + M * e, r = z / np, zl = z % np;
-            st_stream(&peers.recv[r][(((long long) sg.rank * np + zl) * rows + row) * N + x], v[e]);
+            const int z = bo + M * e;
+            cplx *dst = peers.recv[z >> lognp];
+            if (dst != nullptr) st_stream(&dst[(long long) (z & (np - 1)) * zstride + rowoff], v[e]);
         }
         __syncthreads();  // the exchange image is reused by the next tile
+    }
+}
+
+// The same pass with the TMA ring of fft_tile_ring_kernel on the load side: while one tile is transformed and sent,
+// KP of the 16 slices of the CTA's next tile land in shared memory, so the links never wait for the local HBM reads
+// (the plain kernel alternates: load, transform, store).  Tiles come from a device counter.
+template <int N, int T, int KP>
+__global__ void __launch_bounds__(T *(N / 16), 1)
+   fft_tile_p2p_ring_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable peers, const cplx *__restrict__ tw,
+                            unsigned int *__restrict__ counter, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem_ring[];
+    constexpr int M  = N / 16;
+    constexpr int XT = N / T;
+    cplx *S            = reinterpret_cast<cplx *>(smem_ring);
+    cplx *L            = reinterpret_cast<cplx *>(smem_ring + RingSmem<N, T>::EXCHANGE);  // [KP][M][T]
+    uint64_t *mbar     = reinterpret_cast<uint64_t *>(smem_ring + RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx));
+    unsigned int *s_nn = reinterpret_cast<unsigned int *>(mbar + 1);
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    const int rows = sg.na * 2 * sg.h;
+    const long long nstride = (long long) rows * N;
+    const int np = N / sg.G, lognp = FftLog2<N>::value - sg.log2G;
+    const unsigned int ntiles = (unsigned int) (XT * 2 * sg.nly * sg.na);
+    auto issue_ring = [&](unsigned int t) {
+        if (tid == 0) {
+            int xt, a, slot;
+            p2p_tile(sg, XT, t, xt, a, slot);
+            mbar_expect_tx(mbar, (unsigned) (KP * M * T * sizeof(cplx)));
+#pragma unroll
+            for (int e = 0; e < KP; e++) tma_load_4d(L + (size_t) e * M * T, &tmap, xt * 2 * T, a * 2 * sg.h + slot, M * e, 0, mbar);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        s_nn[0] = atomicAdd(counter, 1u);
+        s_nn[1] = atomicAdd(counter, 1u);
+    }
+    __syncthreads();
+    unsigned int cur = s_nn[0], nxt = s_nn[1];
+    __syncthreads();
+    if (cur < ntiles) issue_ring(cur);
+    unsigned int parity = 0;
+    while (cur < ntiles) {
+        if (tid == 0) s_nn[0] = atomicAdd(counter, 1u);  // the tile after next
+        int xt, a, slot;
+        p2p_tile(sg, XT, cur, xt, a, slot);
+        const int row = a * 2 * sg.h + slot;
+        const int x   = xt * T + p;
+        const int y   = slab_row(N, sg.G, sg.rank, slot);
+        const long long base = (long long) row * N + x;
+        const long long rowoff = ((long long) a * N + y) * N + x, zstride = (long long) sg.na * N * N;  // B2[zl][a][y][x]
+        cplx v[16];
+#pragma unroll
+        for (int e = KP; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int e = 0; e < KP; e++) v[e] = L[(size_t) (e * M + b) * T + p];
+        __syncthreads();  // the ring has been read and the exchange image of the previous tile is no longer in use
+        const unsigned int nn = s_nn[0];
+        if (nxt < ntiles) issue_ring(nxt);
+        const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int z = bo + M * e;
+            cplx *dst = peers.recv[z >> lognp];
+            if (dst != nullptr) st_stream(&dst[(long long) (z & (np - 1)) * zstride + rowoff], v[e]);
+        }
+        cur = nxt;
+        nxt = nn;
     }
 }
 
@@ -449,14 +530,14 @@ __device__ __forceinline__ void fold_stats(double (*s_red)[8], int tid, double q
 template <int N, int T, int A, bool RVZEL, bool ACC>
 __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, float *keep, const cplx *__restrict__ tw,
                                             const EmitParams &ep, const RecLayout &L, unsigned char *rec0, long long z, int x,
-                                            int tid, int p, int b, double (*s_red)[8]);
+                                            int tid, int p, int b, double (*s_red)[8], unsigned pslot);
 
 template <int N, int T, int A, bool SLAB, bool RVZEL>
 __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const cplx *__restrict__ next, const SlabGeom &sg, int zl,
                                            cplx *S, float *keep,
                                            const cplx *__restrict__ tw, const EmitParams &ep, const RecLayout &L,
                                            unsigned char *rec0, long long z, int x,
-                                           int tid, int p, int b, bool first, double (*s_red)[8]) {
+                                           int tid, int p, int b, bool first, double (*s_red)[8], unsigned pslot) {
     constexpr int M = N / 16;
     cplx v[16];
 #pragma unroll
@@ -474,7 +555,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
         }
     }
     if (!first) __syncthreads();  // the previous array's last exchange read is complete
-    emit_finish<N, T, A, RVZEL, false>(v, zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, s_red);
+    emit_finish<N, T, A, RVZEL, false>(v, zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, s_red, pslot);
 }
 
 // Transform one packed array of the tile along y (v[e] = row b + M*e on entry), then either park its values or
@@ -483,7 +564,7 @@ __device__ __forceinline__ void emit_array(const cplx *__restrict__ src, const c
 template <int N, int T, int A, bool RVZEL, bool ACC>
 __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, float *keep, const cplx *__restrict__ tw,
                                             const EmitParams &ep, const RecLayout &L, unsigned char *rec0, long long z, int x,
-                                            int tid, int p, int b, double (*s_red)[8]) {
+                                            int tid, int p, int b, double (*s_red)[8], unsigned pslot) {
     constexpr int M  = N / 16;
     constexpr int NT = T * M;
     const int rb = ep.record_bytes, dbl = L.dbl;
@@ -551,7 +632,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                 if (qplt && ep.scratch != nullptr) {
                     // park (displ0, displ1) in this SM's L2-resident scratch: the record is then written whole, as
                     // two back-to-back 16-byte stores, when A3 is done — no partially written 32-byte sectors in L2
-                    park_st2(&reinterpret_cast<float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid],
+                    park_st2(&reinterpret_cast<float2 *>(ep.scratch)[((size_t) pslot * 16 + e) * NT + tid],
                              make_float2((float) v[e].y, (float) v[e].x), pol);
                     continue;
                 }
@@ -573,7 +654,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                 if (qplt && sd != nullptr) {
                     // qPLT (RVdoubleZel): park the displacement in this SM's L2-resident scratch, the whole
                     // 56-byte record is written in one burst when A3 is done
-                    double *q = sd + (((size_t) smid() * 16 + e) * NT + tid) * 3;
+                    double *q = sd + (((size_t) pslot * 16 + e) * NT + tid) * 3;
                     q[0] = v[e].y, q[1] = v[e].x, q[2] = pos0;
                     continue;
                 }
@@ -599,7 +680,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 if (wide && ep.scratch != nullptr) {
-                    const float2 d01 = park_ld2(&reinterpret_cast<const float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid], pol);
+                    const float2 d01 = park_ld2(&reinterpret_cast<const float2 *>(ep.scratch)[((size_t) pslot * 16 + e) * NT + tid], pol);
                     const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
                     st_record32(rec, make_float4(__uint_as_float(w0), __uint_as_float(w1), d01.x, d01.y),
                                 make_float4(park_ld<ACC>(&keep[(0 * 16 + e) * NT + tid], pol), (float) v[e].y, (float) v[e].x,
@@ -607,7 +688,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                     continue;
                 }
                 if (ep.scratch != nullptr) {
-                    const float2 d01 = park_ld2(&reinterpret_cast<const float2 *>(ep.scratch)[((size_t) smid() * 16 + e) * NT + tid], pol);
+                    const float2 d01 = park_ld2(&reinterpret_cast<const float2 *>(ep.scratch)[((size_t) pslot * 16 + e) * NT + tid], pol);
                     const unsigned int w0 = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) y << 16);
                     *reinterpret_cast<float4 *>(rec) = make_float4(__uint_as_float(w0), __uint_as_float(w1), d01.x, d01.y);
                 }
@@ -622,7 +703,7 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
                 const int y = b + M * e;
                 unsigned char *rec = rec0 + (size_t) y * N * rb;
                 if (sd != nullptr) {
-                    const double *q = sd + (((size_t) smid() * 16 + e) * NT + tid) * 3;
+                    const double *q = sd + (((size_t) pslot * 16 + e) * NT + tid) * 3;
                     if (L.off_ijk >= 0)
                         *reinterpret_cast<ushort4 *>(rec + L.off_ijk) =
                            make_ushort4((unsigned short) z, (unsigned short) y, (unsigned short) x, 0);
@@ -651,16 +732,19 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     // z_first counts this rank's planes; the particle id carries the global plane index
     const long long zl = z_first + blockIdx.y;
-    const long long z  = SLAB ? (long long) sg.rank * (N / sg.G) + zl : zl;
+    const long long z  = SLAB ? (long long) sg.rank * (N / sg.G) + zl : zl + ep.zglobal0;
     const int x        = blockIdx.x * T + p;
-    const long long N3 = SLAB ? 0 : (long long) N * N * N;
-    const cplx *src    = SLAB ? cube + x : cube + zl * N * (long long) N + x;  // + B2 row offset  |  + a*N3 + y*N
+    const long long N3 = SLAB ? 0 : ep.astride;
+    const cplx *src    = SLAB ? cube + x : cube + zl * ep.zstride + x;  // + B2 row offset  |  + a*astride + y*N
+    // parking slot of this CTA in the L2-resident scratch: the SM it runs on, read once (the launcher only hands the
+    // scratch out when at most one CTA of the kernel fits an SM)
+    const unsigned pslot = smid();
     const RecLayout L  = rec_layout(ep.icformat);
     unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;  // + y*N*rb
     const bool pf = ep.prefetch;
     const cplx *s0 = src, *s1 = src + N3, *s2 = src + 2 * N3, *s3 = src + 3 * N3;
 #define ZPLT_EA(A, SRC, NEXT, FIRST) \
-    emit_array<N, T, A, SLAB, RVZEL>(SRC, pf ? (NEXT) : nullptr, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, FIRST, s_red)
+    emit_array<N, T, A, SLAB, RVZEL>(SRC, pf ? (NEXT) : nullptr, sg, (int) zl, S, keep, tw, ep, L, rec0, z, x, tid, p, b, FIRST, s_red, pslot)
     if constexpr (RVZEL) {
         // RVZel: A0 and A2 first (two parked floats), then A1 and A3 complete the two 16-byte halves
         if (ep.qPLT) {
@@ -714,18 +798,21 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
     cplx *L            = reinterpret_cast<cplx *>(smem_ring + RingSmem<N, T>::EXCHANGE);  // [KP][M][T]
     uint64_t *mbar     = reinterpret_cast<uint64_t *>(smem_ring + RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx));
     unsigned int *s_nn = reinterpret_cast<unsigned int *>(mbar + 1);
-    float *keep        = keep_all + (size_t) smid() * (ZPLT_KEEP_BYTES / sizeof(float));
+    // parking areas are indexed by CTA (grid <= SM count <= 256 slots), not by %smid: nothing guarantees one CTA per SM
+    float *keep        = keep_all + (size_t) blockIdx.x * (ZPLT_KEEP_BYTES / sizeof(float));
+    const unsigned pslot = blockIdx.x;
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     const unsigned int ntiles = (unsigned int) (XT * nz);
     const RecLayout Lr = rec_layout(ep.icformat);
-    const long long N3 = (long long) N * N * N;
+    const long long N3 = ep.astride;
     const bool qplt    = ep.qPLT;
+    const bool za_order = ep.zstride > ep.astride;  // slab layout [zl][a][y][x]: the tensor map's dimensions are (x, y, a, zl)
     auto issue_ring = [&](unsigned int t, int a) {
         if (tid == 0) {
             mbar_expect_tx(mbar, (unsigned) (KP * M * T * sizeof(cplx)));
             const int tx = t % XT, zl = (int) z_first + (int) (t / XT);
 #pragma unroll
-            for (int e = 0; e < KP; e++) tma_load_4d(L + (size_t) e * M * T, &tmap, tx * 2 * T, M * e, zl, a, mbar);
+            for (int e = 0; e < KP; e++) tma_load_4d(L + (size_t) e * M * T, &tmap, tx * 2 * T, M * e, za_order ? a : zl, za_order ? zl : a, mbar);
         }
     };
     for (int i = tid; i < 32 * 8; i += NT) (&s_red[0][0])[i] = 0.0;
@@ -743,7 +830,7 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         if (tid == 0) s_nn[0] = atomicAdd(counter, 1u);  // the tile after next
         const int x        = (int) (cur % XT) * T + p;
         const long long zl = z_first + cur / XT;
-        const cplx *src    = cube + zl * N * (long long) N + x;
+        const cplx *src    = cube + zl * ep.zstride + x;
         unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * ep.record_bytes;
         // one unit: array A of this tile; NEXT_T / NEXT_A name the unit whose slices are requested meanwhile
 #define ZPLT_UNIT(A, NEXT_OK, NEXT_T, NEXT_A)                                                                          \
@@ -756,7 +843,7 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         __syncthreads(); /* ring consumed; the previous unit's last exchange read is complete */                      \
         if ((A) == 0) nn = s_nn[0];                                                                                    \
         if (NEXT_OK) issue_ring(NEXT_T, NEXT_A);                                                                       \
-        emit_finish<N, T, A, RVZEL, true>(v, (int) zl, S, keep, tw, ep, Lr, rec0, zl, x, tid, p, b, s_red);            \
+        emit_finish<N, T, A, RVZEL, true>(v, (int) zl, S, keep, tw, ep, Lr, rec0, zl + ep.zglobal0, x, tid, p, b, s_red, pslot); \
     }
         if constexpr (RVZEL) {
             // RVZel: A0 and A2 first (two parked floats), then A1 and A3 complete the two 16-byte halves
@@ -798,14 +885,8 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
 }
 
 // ------------------------------------------------------------------ dispatch -------
-static int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
 // pencils per CTA for the in-place strided/row passes
 int fft_tile_T(int N) {
-    int t = env_int("ZPLT_TILE_T", 0);
-    if (t) return t;
     switch (N) {
         case 16: return 16;
         case 32: return 32;
@@ -821,25 +902,18 @@ int fft_tile_T(int N) {
 size_t fft_tile_smem(int N, int T) { return (size_t) T * (N + (T >= 8 ? 1 : (T == 4 ? 2 : 4))) * sizeof(cplx); }
 
 // CTAs that fit on the device at once (persistent kernels launch exactly that many)
-static int persistent_ctas(const void *func, int threads, size_t smem) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+static int persistent_ctas(const void *func, int threads, size_t smem, int sms) {
+    int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem);
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
 
-static unsigned int *tile_counter(cudaStream_t st) {
-    // one 4-byte work counter per launch, rotating through a small device array so that launches in flight on
-    // different streams never share one
-    static unsigned int *ctr[16] = {nullptr};
-    static int next[16] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) return nullptr;
-    if (!ctr[dev] && cudaMalloc((void **) &ctr[dev], 64 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    unsigned int *c = ctr[dev] + (next[dev]++ & 63);
+// one 4-byte work counter per launch, rotating through the context's small device array so that launches in flight on
+// different streams never share one
+static unsigned int *tile_counter(LaunchRes &lr, cudaStream_t st) {
+    if (!lr.counters) return nullptr;
+    unsigned int *c = lr.counters + (lr.next_counter++ & 63);
     if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) return nullptr;
     return c;
 }
@@ -867,19 +941,16 @@ static int encode_tmap4(CUtensorMap *tmap, const void *base, const cuuint64_t di
 }
 
 template <int N, int T, int KP>
-static int launch_tiles_ring_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
+static int launch_tiles_ring_t(cplx *data, const TileGeom &g, const cplx *tw, LaunchRes &lr, cudaStream_t st) {
     constexpr int M = N / 16;
     const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 16;
     cudaError_t e = cudaFuncSetAttribute(fft_tile_ring_kernel<N, T, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    unsigned int *ctr = tile_counter(st);
+    unsigned int *ctr = tile_counter(lr, st);
     if (!ctr) return (int) cudaErrorMemoryAllocation;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntiles = (long long) g.grid_x * g.grid_y * g.grid_z;
     if (ntiles >= (1ll << 31)) return (int) cudaErrorInvalidValue;
-    const long long nctas = ntiles < sms ? ntiles : sms;
+    const long long nctas = ntiles < lr.sms ? ntiles : lr.sms;
     // the data as a 4-D tensor of doubles: (x, rows of the outer index, transform axis, array)
     CUtensorMap tmap;
     const cuuint64_t dims[4]    = {(cuuint64_t) 2 * T * g.grid_x, (cuuint64_t) g.grid_y, (cuuint64_t) N, (cuuint64_t) g.grid_z};
@@ -892,17 +963,23 @@ static int launch_tiles_ring_t(cplx *data, const TileGeom &g, const cplx *tw, cu
     return (int) cudaGetLastError();
 }
 
+// sizes that have the ring-prefetched kernels instantiated (register file = one tile, shared memory = exchange image + ring)
 template <int N, int T>
-static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
-    // ring-prefetched variant for unit-stride tiles (the z pass and the plain y pass); ZPLT_ZRING = slices to prefetch
-    if constexpr ((N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32)) {
-        const int kp = env_int("ZPLT_ZRING", 12);  // measured at PPD=1024: z pass 33.9 ms without, 29.9 / 28.1 / 27.5 ms with 4 / 8 / 12 slices
-        if (kp > 0 && g.plo_stride == 1 && g.pa == T && g.tstride == T && g.phi_stride == 0) {
+constexpr bool has_ring() {
+    return (N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32);
+}
+
+template <int N, int T>
+static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st) {
+    // ring-prefetched variant for unit-stride tiles (the z pass and the plain y pass); Tuning::zring = slices to prefetch
+    if constexpr (has_ring<N, T>()) {
+        const int kp = tn.zring;  // measured at PPD=1024: z pass 33.9 ms without, 29.9 / 28.1 / 27.5 ms with 4 / 8 / 12 slices
+        if (kp > 0 && lr.counters && g.plo_stride == 1 && g.pa == T && g.tstride == T && g.phi_stride == 0) {
             if constexpr (N == 1024) {
-                if (kp < 8) return launch_tiles_ring_t<N, T, 4>(data, g, tw, st);
-                if (kp < 12) return launch_tiles_ring_t<N, T, 8>(data, g, tw, st);
+                if (kp < 8) return launch_tiles_ring_t<N, T, 4>(data, g, tw, lr, st);
+                if (kp < 12) return launch_tiles_ring_t<N, T, 8>(data, g, tw, lr, st);
             }
-            return launch_tiles_ring_t<N, T, 12>(data, g, tw, st);
+            return launch_tiles_ring_t<N, T, 12>(data, g, tw, lr, st);
         }
     }
     size_t smem = fft_tile_smem(N, T);
@@ -914,13 +991,14 @@ static int launch_tiles_t(cplx *data, const TileGeom &g, const cplx *tw, cudaStr
 }
 
 template <int N, int NP>
-static int launch_genx_t(const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st) {
+static int launch_genx_t(const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, const Tuning &tn, LaunchRes &lr,
+                         bool skip_fft, cudaStream_t st) {
     if ((2 * g.na) % NP) return (int) cudaErrorInvalidValue;
     size_t smem = fft_tile_smem(N, NP) + (size_t) 6 * N * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gen_xfft_kernel<N, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
     dim3 grid(N, sg.G == 1 ? N / 2 + 1 : sg.nly + ((sg.rank == 0 && sg.ly0 == 0) ? 1 : 0), 1);
-    gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, sg, cube, tw);
+    gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, sg, cube, tw, skip_fft ? 1 : 0);
     return (int) cudaGetLastError();
 }
 
@@ -929,97 +1007,111 @@ static int launch_genx_t(const GenParams &g, const SlabGeom &sg, cplx *cube, con
 
 // pencils transformed concurrently by one CTA of the generation + x-FFT kernel (divides 2*narray)
 int gen_xfft_T(int N, int na) {
-    int t = env_int("ZPLT_GENX_T", 0);
-    if (t) return t;
     switch (N) {
         case 512: return na == 4 ? 8 : 4;
         default: return 4;  // N = 2048: 4 pencils (131 KB) + mode state (96 KB) = 229.5 KB, just inside the 227 KiB limit
     }
 }
 
-int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st) {
-    ZPLT_CASE(launch_genx_t, 16, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 32, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 64, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 128, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 256, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 512, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 512, 8, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 1024, 8, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 1024, 4, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 1024, 2, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 2048, 2, g, sg, cube, tw, st)
-    ZPLT_CASE(launch_genx_t, 2048, 4, g, sg, cube, tw, st)
+int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, const Tuning &tn, LaunchRes &lr,
+                    bool skip_fft, cudaStream_t st) {
+    ZPLT_CASE(launch_genx_t, 16, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 32, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 64, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 128, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 256, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 512, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 512, 8, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 1024, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
+    ZPLT_CASE(launch_genx_t, 2048, 4, g, sg, cube, tw, tn, lr, skip_fft, st)
     return (int) cudaErrorInvalidValue;
 }
 
 template <int N, int T>
-static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, cudaStream_t st) {
-    size_t smem = fft_tile_smem(N, T);
-    cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return (int) e;
+static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,
+                              LaunchRes &lr, cudaStream_t st) {
     PeerTable pt;
     for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
     const long long ntiles = (long long) (N / T) * 2 * sg.nly * sg.na;
-    long long nctas = persistent_ctas((const void *) fft_tile_p2p_kernel<N, T>, T * (N / 16), smem);
-    // about two thirds of the SMs keep NVLink saturated and leave room for the overlapped generation kernel.  At N = 2048
-    // (4-pencil tiles, 64-byte peer stores) the pass is bound by NVLink's efficiency with 64-byte writes (~355 GB/s per GPU),
-    // not by SMs: 8 GPUs, PPD=2048, 197.5 ms/step with the cap and 207.9 ms without it.
-    const int lim = env_int("ZPLT_P2P_CTAS", 96);  // 0: as many as fit
+    // about two thirds of the SMs keep NVLink saturated and leave room for the overlapped generation kernel
+    const int lim = tn.p2p_ctas;  // 0: as many as fit
+    if constexpr (has_ring<N, T>()) {
+        if (tn.slab_ring > 0 && lr.counters && ntiles < (1ll << 31)) {
+            constexpr int M = N / 16, KP = 12;
+            const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 16;
+            cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_ring_kernel<N, T, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) return (int) e;
+            unsigned int *ctr = tile_counter(lr, st);
+            if (!ctr) return (int) cudaErrorMemoryAllocation;
+            long long nctas = lr.sms;
+            if (lim > 0 && lim < nctas) nctas = lim;
+            if (nctas > ntiles) nctas = ntiles;
+            // the stage-1 buffer B1[z][row][x] as a tensor of doubles (x, row, z, 1)
+            const int rows = sg.na * 2 * sg.h;
+            CUtensorMap tmap;
+            const cuuint64_t dims[4]    = {(cuuint64_t) 2 * N, (cuuint64_t) rows, (cuuint64_t) N, 1};
+            const cuuint64_t strides[3] = {(cuuint64_t) N * sizeof(cplx), (cuuint64_t) rows * N * sizeof(cplx),
+                                           (cuuint64_t) rows * N * N * sizeof(cplx)};
+            const cuuint32_t box[4]     = {2 * T, 1, (cuuint32_t) M, 1};
+            if (int rc = encode_tmap4(&tmap, b1, dims, strides, box)) return rc;
+            fft_tile_p2p_ring_kernel<N, T, KP><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw, ctr, tmap);
+            return (int) cudaGetLastError();
+        }
+    }
+    size_t smem = fft_tile_smem(N, T);
+    cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    long long nctas = persistent_ctas((const void *) fft_tile_p2p_kernel<N, T>, T * (N / 16), smem, lr.sms);
     if (lim > 0 && lim < nctas) nctas = lim;
     if (nctas > ntiles) nctas = ntiles;
     fft_tile_p2p_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw);
     return (int) cudaGetLastError();
 }
 
-int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
-                         cudaStream_t st) {
+int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,
+                         LaunchRes &lr, cudaStream_t st) {
     if (sg.G > 16) return (int) cudaErrorInvalidValue;
-    ZPLT_CASE(launch_tiles_p2p_t, 32, 32, b1, sg, peer_recv, tw, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 64, 32, b1, sg, peer_recv, tw, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 128, 16, b1, sg, peer_recv, tw, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 256, 16, b1, sg, peer_recv, tw, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 512, 8, b1, sg, peer_recv, tw, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 1024, 8, b1, sg, peer_recv, tw, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 2048, 4, b1, sg, peer_recv, tw, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 32, 32, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 64, 32, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 128, 16, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 256, 16, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 512, 8, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 1024, 8, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 2048, 4, b1, sg, peer_recv, tw, tn, lr, st)
     return (int) cudaErrorInvalidValue;
 }
 
-int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &g, const cplx *tw, cudaStream_t st) {
-    ZPLT_CASE(launch_tiles_t, 16, 16, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 32, 32, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 64, 32, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 128, 16, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 256, 16, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 256, 8, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 512, 8, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 512, 4, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 1024, 8, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 1024, 4, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 1024, 2, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 2048, 4, data, g, tw, st)
-    ZPLT_CASE(launch_tiles_t, 2048, 2, data, g, tw, st)
+int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &g, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st) {
+    ZPLT_CASE(launch_tiles_t, 16, 16, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 32, 32, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 64, 32, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 128, 16, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 256, 16, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 512, 8, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 1024, 8, data, g, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_t, 2048, 4, data, g, tw, tn, lr, st)
     return (int) cudaErrorInvalidValue;
 }
 
 template <int N, int T, bool RVZEL, int KP>
-static int launch_emit_ring_t(const cplx *cube, int na, long long z_first, long long nz, const EmitParams &ep, const cplx *tw,
+static int launch_emit_ring_t(const cplx *cube, long long z_first, long long nz, const EmitParams &ep, const cplx *tw, LaunchRes &lr,
                               cudaStream_t st) {
     constexpr int M = N / 16;
     const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 16;
     cudaError_t e = cudaFuncSetAttribute(fft_emit_ring_kernel<N, T, RVZEL, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    unsigned int *ctr = tile_counter(st);
+    unsigned int *ctr = tile_counter(lr, st);
     if (!ctr) return (int) cudaErrorMemoryAllocation;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntiles = (long long) (N / T) * nz;
-    const long long nctas  = ntiles < sms ? ntiles : sms;
-    // the cube [a][z][y][x] as a tensor of doubles (x, y = transform axis, z, a)
+    long long nctas        = ntiles < lr.sms ? ntiles : lr.sms;
+    if (nctas > 256) nctas = 256;  // parking slots (ZPLT_SCRATCH_BYTES)
+    // the planes as a tensor of doubles: (x, y = transform axis, then z and a in the order of their strides)
     CUtensorMap tmap;
-    const cuuint64_t dims[4]    = {(cuuint64_t) 2 * N, (cuuint64_t) N, (cuuint64_t) N, (cuuint64_t) na};
-    const cuuint64_t strides[3] = {(cuuint64_t) N * sizeof(cplx), (cuuint64_t) N * N * sizeof(cplx), (cuuint64_t) N * N * N * sizeof(cplx)};
+    const bool za = ep.zstride > ep.astride;
+    const cuuint64_t d2 = za ? (cuuint64_t) ep.na : (cuuint64_t) ep.nzl, d3 = za ? (cuuint64_t) ep.nzl : (cuuint64_t) ep.na;
+    const cuuint64_t s2 = za ? (cuuint64_t) ep.astride : (cuuint64_t) ep.zstride, s3 = za ? (cuuint64_t) ep.zstride : (cuuint64_t) ep.astride;
+    const cuuint64_t dims[4]    = {(cuuint64_t) 2 * N, (cuuint64_t) N, d2, d3};
+    const cuuint64_t strides[3] = {(cuuint64_t) N * sizeof(cplx), s2 * sizeof(cplx), s3 * sizeof(cplx)};
     const cuuint32_t box[4]     = {2 * T, (cuuint32_t) M, 1, 1};
     if (int rc = encode_tmap4(&tmap, cube, dims, strides, box)) return rc;
     float *keep_all = reinterpret_cast<float *>(static_cast<unsigned char *>(ep.scratch) + ZPLT_SCRATCH_PARK_BYTES);
@@ -1027,17 +1119,19 @@ static int launch_emit_ring_t(const cplx *cube, int na, long long z_first, long 
     return (int) cudaGetLastError();
 }
 
+// slab: the planes are in the per-source layout B2[src][zl][a][slot][x] of the caller-run all-to-all (zplt_slab.h); otherwise
+// EmitParams describes them (single-GPU cube, or a slab rank's [zl][a][y][x] after the fused exchange)
 template <int N, int T>
-static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long z_first, long long nz, const EmitParams &ep,
-                                 const cplx *tw, cudaStream_t st, int *launches) {
-    if constexpr ((N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32)) {
-        // persistent ring-prefetched form (single GPU, records wanted, parking space present); ZPLT_YRING=0 disables
-        if (sg.G == 1 && ep.out != nullptr && ep.scratch != nullptr && env_int("ZPLT_YRING", 12) > 0) {
+static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, bool slab, long long z_first, long long nz, const EmitParams &ep,
+                                 const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st, int *launches) {
+    if constexpr (has_ring<N, T>()) {
+        // persistent ring-prefetched form (records wanted, parking space present); Tuning::yring = 0 disables
+        if (!slab && ep.out != nullptr && ep.scratch != nullptr && lr.counters && tn.yring > 0) {
             // measured at PPD=1024: RVZel qPLT 28.9 -> 28.4 ms, ZA 20.5 -> 19.3 ms; the double formats lose (RVdoubleZel
             // 58.0 -> 66.9 ms: the ring kernel's record bursts spill registers), so they keep the one-tile-per-CTA kernel
-            if (ep.icformat == 1 || env_int("ZPLT_YRING", 12) > 100) {
-                int rc = (ep.icformat == 1) ? launch_emit_ring_t<N, T, true, 12>(cube, ep.na, z_first, nz, ep, tw, st)
-                                            : launch_emit_ring_t<N, T, false, 12>(cube, ep.na, z_first, nz, ep, tw, st);
+            if (ep.icformat == 1 || tn.yring > 100) {
+                int rc = (ep.icformat == 1) ? launch_emit_ring_t<N, T, true, 12>(cube, z_first, nz, ep, tw, lr, st)
+                                            : launch_emit_ring_t<N, T, false, 12>(cube, z_first, nz, ep, tw, lr, st);
                 if (launches) *launches += 1;
                 return rc;
             }
@@ -1045,7 +1139,7 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long
     }
     size_t smem = fft_tile_smem(N, T) + (size_t) 2 * 16 * T * (N / 16) * sizeof(float);
     dim3 grid(N / T, (unsigned) nz, 1);
-    const bool slab = sg.G > 1, rvzel = ep.icformat == 1;
+    const bool rvzel = ep.icformat == 1;
     EmitParams ep2 = ep;
     if (ep2.scratch != nullptr) {
         // the per-SM parking space is only safe when CTAs of this kernel never share an SM, and large enough only up to 512 threads
@@ -1058,7 +1152,7 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, true, false>, T * (N / 16), smem);
         else
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_emit_strided_kernel<N, T, false, false>, T * (N / 16), smem);
-        if (per_sm != 1 || T * (N / 16) > 512 || !ep.qPLT) ep2.scratch = nullptr;
+        if (per_sm != 1 || T * (N / 16) > 512 || !ep.qPLT || lr.sms > 256) ep2.scratch = nullptr;
     }
 #define ZPLT_EMIT_LAUNCH(SL, RV)                                                                                              \
     {                                                                                                                         \
@@ -1076,17 +1170,19 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, long long
     return (int) cudaGetLastError();
 }
 
-// y-axis FFT + record emission for planes [z_first, z_first+nz); the cube holds the x- and z-transformed arrays
+// y-axis FFT + record emission for planes [z_first, z_first+nz); the planes hold the x- and z-transformed arrays.
+// ep.astride == 0 selects the per-source slab layout (SlabGeom), otherwise EmitParams::astride/zstride describe the planes.
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
-                            const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches) {
-    ZPLT_CASE(launch_emit_strided_t, 16, 16, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 32, 32, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 64, 32, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 128, 16, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 256, 16, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 512, 8, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, sg, z_first, nz, ep, tw, st, launches)
-    ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, sg, z_first, nz, ep, tw, st, launches)
+                            const EmitParams &ep, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st, int *launches) {
+    const bool slab = ep.astride == 0;
+    ZPLT_CASE(launch_emit_strided_t, 16, 16, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 32, 32, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 64, 32, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 128, 16, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 256, 16, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 512, 8, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 1024, 8, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
+    ZPLT_CASE(launch_emit_strided_t, 2048, 4, cube, sg, slab, z_first, nz, ep, tw, tn, lr, st, launches)
     return (int) cudaErrorInvalidValue;
 }
 

@@ -32,7 +32,12 @@ struct EmitParams {
     double *stats;      // [ZPLT_STAT_SLOTS][8]: sum dens^2, +max[3], -max[3], pad
     int prefetch;       // L2-prefetch the next packed array of the tile during the transform
     int wide_records;   // RVZel + qPLT: write each 32-byte record with one 256-bit store; -1 = default (ring kernel only), 0 off, 1 on
-    void *scratch;      // per-SM, L2-resident parking space [sm][16][threads] x 24 B (qPLT, one CTA per SM), or NULL
+    void *scratch;      // per-CTA-slot, L2-resident parking space [slot][16][threads] x 24 B (qPLT, one CTA per SM), or NULL
+    // where the planes live (complex elements): packed array a of local plane zl starts at a*astride + zl*zstride, rows are N apart.
+    // Single GPU: the cube [a][z][y][x] (astride = N^3, zstride = N^2).  Slab rank after the fused exchange: [zl][a][y][x]
+    // (astride = N^2, zstride = na*N^2).  zglobal0 = global index of local plane 0 (particle ids carry global z).
+    long long astride, zstride, zglobal0;
+    int nzl;            // local planes held
 };
 #define ZPLT_STAT_SLOTS 64
 // EmitParams::scratch: [256 SMs][16][512 threads] x 24 B of record parking, then [256 SMs] x 64 KB that replace the
@@ -40,25 +45,50 @@ struct EmitParams {
 #define ZPLT_SCRATCH_PARK_BYTES ((size_t) 256 * 16 * 512 * 24)
 #define ZPLT_SCRATCH_BYTES (ZPLT_SCRATCH_PARK_BYTES + (size_t) 256 * 65536)
 
+// Tuning / diagnostic switches of a context.  Defaults come from the environment (ZPLT_<NAME>) ONCE, in zplt_create;
+// zplt_set_option changes them afterwards.  Nothing on the launch path calls getenv.
+struct Tuning {
+    int zring        = 12;  // ZPLT_ZRING: slices of the next tile the ring-prefetched strided pass requests through TMA (0 = plain kernel)
+    int yring        = 12;  // ZPLT_YRING: the same for the y pass + emission (0 = one tile per CTA)
+    int wide_records = -1;  // ZPLT_WIDE_RECORDS: 256-bit RVZel record stores; -1 = where measured (ring kernels), 0 off, 1 on
+    int emit_scratch = 1;   // ZPLT_EMIT_SCRATCH: park record halves in the L2-resident scratch (whole-record stores)
+    int emit_prefetch = 1;  // ZPLT_EMIT_PREFETCH: L2-prefetch the next packed array of a tile (one-tile-per-CTA kernel)
+    int slab_groups  = 8;   // ZPLT_SLAB_GROUPS: row groups of stage 1 on a slab rank (generation of group j+1 overlaps the z pass of j)
+    int p2p_ctas     = 96;  // ZPLT_P2P_CTAS: CTAs of the z pass + exchange kernel (0 = as many as fit)
+    int dit2048      = 0;   // ZPLT_DIT2048: 8-pencil decimation kernels for the N = 2048 strided passes
+    int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
+    int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
+};
+
+// Per-context launch resources: the work counters of the persistent kernels (a small rotating device array, so that
+// launches in flight on different streams never share one) and the device's SM count.
+struct LaunchRes {
+    unsigned int *counters = nullptr;  // [64]
+    int next_counter       = 0;
+    int sms                = 0;
+};
+
 int fft_tile_T(int N);            // pencils per CTA used for length N (strided / row kernels)
 int gen_xfft_T(int N, int na);    // pencils per CTA of the generation + x-FFT kernel
 size_t fft_tile_smem(int N, int T);
-// Fused mode generation + x-axis FFT, writes the whole [na][z][y][x] cube.
-int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, cudaStream_t st);
+// Fused mode generation + x-axis FFT, writes the whole [na][z][y][x] cube (skip_fft: the packed arrays as the
+// kernel forms them, without the transform — introspection of the hot kernel).
+int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, const Tuning &tn, LaunchRes &lr,
+                    bool skip_fft, cudaStream_t st);
 // In-place backward FFT of every pencil described by geom (tiles of T pencils).  Returns cudaError_t.
-int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st);
 // z-axis FFT of a slab rank's stage-1 buffer with the exchange fused in: results are stored
-// directly into every owner rank's stage-2 buffer (peer_recv[r], NVLink peer memory).
-int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
-                         cudaStream_t st);
-// The same two launchers behind a switch: with ZPLT_DIT2048=1 and N = 2048 they use the 8-pencil decimation kernels of
-// zplt_fft2048_kernels.cu (experimental, see that file); otherwise they forward to the launchers above.
-int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, cudaStream_t st);
+// directly into every owner rank's stage-2 buffer (peer_recv[r], NVLink peer memory; NULL = discard).
+int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,
+                         LaunchRes &lr, cudaStream_t st);
+// The same two launchers behind Tuning::dit2048: at N = 2048 they use the 8-pencil decimation kernels of
+// zplt_fft2048_kernels.cu; otherwise they forward to the launchers above.
+int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st);
 int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
-                             cudaStream_t st);
+                             const Tuning &tn, LaunchRes &lr, cudaStream_t st);
 // y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
-                            const EmitParams &ep, const cplx *tw, cudaStream_t st, int *launches);
+                            const EmitParams &ep, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st, int *launches);
 
 int launch_power_table(double *ptab, long long count, double fundamental2, int is_powerlaw, double index, int n,
                        const double *x, const double *y, const double *y2, double normalization, double smooth2,

@@ -34,6 +34,9 @@ class SlabWorkspace:
         self.send = self.buf[:half]
         self.recv = self.buf[half:]
 
+    def begin(self):
+        """Nothing to wait for: the all-to-all below is ordered on the stream after this rank's emission."""
+
     def exchange(self, group=None):
         """Run the all-to-all on the current torch stream and mark the context as exchanged."""
         exchange_tensors(self.send, self.recv, group)
@@ -58,6 +61,20 @@ class PeerExchange:
         handles = [None] * world
         dist.all_gather_object(handles, mine, group=group)
         ctx.ipc_import(handles)
+
+    def close(self):
+        """Unmap the peers' buffers on every rank; only then may any rank free (or destroy the context that owns) its own."""
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)
+        self.ctx.ipc_close()
+        dist.barrier(group=self.group)
+
+    def begin(self):
+        """Call before ctx.generate() of every step but the first: the peers' z pass of the coming step stores into the
+        receive buffer this rank may still be emitting planes from (write-after-read), so everybody first finishes
+        emitting, then everybody may generate."""
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)
 
     def exchange(self):
         """Call after ctx.generate(): wait for this rank's peer stores, then for everybody else's."""

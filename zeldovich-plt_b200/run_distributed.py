@@ -64,6 +64,7 @@ def main():
         ctx.generate()
     elif args.exchange == "p2p":
         ex = zd.PeerExchange(ctx)
+        ex.begin()
         ctx.generate()
         ex.exchange()
     else:
@@ -78,29 +79,53 @@ def main():
 
     z0, z1 = zd.plane_range(N, rank, world)
     fileno = lambda z: z * cpd // N
-    shared = z0 > 0 and fileno(z0) == fileno(z0 - 1)
+    qdensity, qoneslab = P.qdensity, P.qoneslab
+    records = qdensity != 2  # ZD_qdensity = 2: density only, no ic_* files (reference src/zeldovich.cpp:871-876, output.cpp:207-224)
+    # ZD_qoneslab >= 0: only that plane is written (reference src/zeldovich.cpp:669), by the rank that owns it
+    w0, w1 = (z0, z1) if qoneslab < 0 else (max(z0, qoneslab), min(z1, qoneslab + 1))
+    shared = records and w0 < w1 and w0 > 0 and qoneslab < 0 and fileno(w0) == fileno(w0 - 1)
     nshared = 0
     if shared:
-        while z0 + nshared < z1 and fileno(z0 + nshared) == fileno(z0):
+        while w0 + nshared < w1 and fileno(w0 + nshared) == fileno(w0):
             nshared += 1
     plane = N * N * rb
-    chunk = max(1, min(z1 - z0, (1 << 30) // plane))
+    dplane = N * N * 4
+    chunk = max(1, min(max(1, w1 - w0), (1 << 30) // plane))
     pinned = torch.empty(chunk * plane, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
+    # density planes (float32 Re A0, reference src/output.cpp:196,217-224) are kept per rank and appended in rank order below
+    dens_parts = []
 
     def write_planes(za, zb):
         for c0 in range(za, zb, chunk):
             n = min(chunk, zb - c0)
-            ctx.fetch_planes_ptr(c0 - z0, n, pinned.data_ptr())
-            for i in range(n):
+            if qdensity:
+                rec, dens = ctx.fetch_planes_density(c0 - z0, n, records=records)
+                dens_parts.append((c0, dens.copy()))
+                if records:
+                    host[:n * plane] = rec.view(np.uint8)
+            else:
+                ctx.fetch_planes_ptr(c0 - z0, n, pinned.data_ptr())
+            for i in range(n if records else 0):
                 with open(os.path.join(outdir, f"ic_{fileno(c0 + i)}"), "ab") as f:
                     f.write(host[i * plane:(i + 1) * plane].tobytes())
 
-    write_planes(z0 + nshared, z1)  # files that start inside this rank's range: no ordering constraint
+    if w0 < w1:
+        write_planes(w0 + nshared, w1)  # files that start inside this rank's range: no ordering constraint
     for turn in range(world):       # the leading planes that continue the previous rank's last file, in rank order
         if rank == turn and nshared:
-            write_planes(z0, z0 + nshared)
+            write_planes(w0, w0 + nshared)
         dist.barrier()
+    if qdensity:
+        # one density file, planes in ascending z: rank 0 creates it ("wb", reference src/output.cpp:282-288), the others append in turn
+        name = P.density_filename.replace("{:d}", str(N))
+        dpath = os.path.join(outdir, name)
+        for turn in range(world):
+            if rank == turn:
+                with open(dpath, "wb" if rank == 0 else "ab") as f:
+                    for _, d in sorted(dens_parts, key=lambda t: t[0]):
+                        f.write(d.tobytes())
+            dist.barrier()
     t2 = time.perf_counter()
     st = ctx.stats()
     stats = torch.tensor([st["density_variance"], *st["max_disp"]], dtype=torch.float64, device=dev)
@@ -113,8 +138,9 @@ def main():
             v = s[1:].cpu().numpy()
             md = np.where(np.abs(v) > np.abs(md), v, md)
         print(f"The rms density variation of the pixels is {np.sqrt(var / N**3):f}", file=sys.stderr)
-        print(f"The maximum component-wise displacements are ({md[0]:g}, {md[1]:g}, {md[2]:g}), same units as BoxSize.",
-              file=sys.stderr)
+        if qdensity != 2:  # reference src/zeldovich.cpp:998
+            print(f"The maximum component-wise displacements are ({md[0]:g}, {md[1]:g}, {md[2]:g}), same units as BoxSize.",
+                  file=sys.stderr)
         print(f"zeldovich took {t2 - t0:.4g} sec for ppd {N} on {world} GPUs ==> {N**3 / 1e6 / (t2 - t0):.3g} Mpart/sec "
               f"(device {t1 - t0:.3g} s, writing {t2 - t1:.3g} s)", file=sys.stderr)
     ctx.close()
