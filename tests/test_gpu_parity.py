@@ -274,7 +274,7 @@ def test_hot_generation_kernel_draws_bit_exact(pkg, oracle, ppd, kc, na4):
         # every site of a run that holds an unmasked site consumes its draws; runs are 16/NP sites (2, 4 or 8) — compare the unmasked ones
         assert np.array_equal(raw[z, y][~masked], want[~masked]), (y, z)
         checked += int((~masked).sum())
-    assert checked > 1000
+    assert checked > 500
 
 
 # ---------------------------------------------------------------- benchmark sizes ---
@@ -587,6 +587,7 @@ def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit):
         for src in range(G):
             c = ctx_from(pkg, P, power, src, G)
             c.set_option("dit2048", dit)
+            c.set_option("dit2048_emit", dit)
             c.set_workspace(W.data_ptr(), ws)
             c.dbg_set_peers([recv if r == target else None for r in range(G)])
             c.generate()

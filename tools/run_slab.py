@@ -61,6 +61,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     if args.p2p:
         ws = zd.PeerExchange(ctx)
+        ws.begin()
         ctx.generate()
         ws.exchange()
     else:
@@ -71,6 +72,8 @@ def main():
         stream.synchronize()
     mine = ctx.fetch_planes(0, N // world)
     st = ctx.stats()
+    if args.p2p:
+        ws.close()
     ctx.close()
     del ws
     if args.oversample_check:

@@ -125,7 +125,7 @@ static void tuning_from_env(Tuning &t) {
         int *v;
     } tab[] = {{"ZPLT_ZRING", &t.zring},           {"ZPLT_YRING", &t.yring},           {"ZPLT_WIDE_RECORDS", &t.wide_records},
                {"ZPLT_EMIT_SCRATCH", &t.emit_scratch}, {"ZPLT_EMIT_PREFETCH", &t.emit_prefetch}, {"ZPLT_SLAB_GROUPS", &t.slab_groups},
-               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_SLAB_RING", &t.slab_ring},
+               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring},
                {"ZPLT_GEN_PERSIST", &t.gen_persist}};
     for (auto &e : tab) {
         const char *s = getenv(e.name);
@@ -141,7 +141,7 @@ extern "C" int zplt_set_option(zplt_ctx *c, const char *name, int32_t value) {
         int *v;
     } tab[] = {{"zring", &t.zring},           {"yring", &t.yring},           {"wide_records", &t.wide_records},
                {"emit_scratch", &t.emit_scratch}, {"emit_prefetch", &t.emit_prefetch}, {"slab_groups", &t.slab_groups},
-               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"slab_ring", &t.slab_ring},
+               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring},
                {"gen_persist", &t.gen_persist}};
     for (auto &e : tab)
         if (!strcmp(e.name, name)) {
@@ -964,7 +964,7 @@ extern "C" int zplt_dbg_fft_variant(int32_t n, int64_t batch, int32_t row_mode, 
     if (!host_data) return fail(ZPLT_EINVAL, "null argument");
     Tuning tn;
     LaunchRes lr;
-    if (variant == 1) tn.zring = 0;
+    if (variant == 1) tn.zring = 0, tn.dit2048 = 0;
     if (variant == 2) tn.dit2048 = 1;
     const int T = fft_tile_T(n);
     if (T == 0) return fail(ZPLT_EINVAL, "unsupported FFT length %d", n);

@@ -18,15 +18,10 @@
 // src/zeldovich.cpp:93-114, and BlockArray::StoreBlock/LoadBlock, src/block_array.cpp:387-414, 466-504).
 #include "zplt_fft.cuh"
 #include "zplt_internal.h"
+#include "zplt_kernel_util.cuh"
 
 namespace zplt {
 namespace {
-
-__device__ __forceinline__ cplx ld_stream2(const cplx *p) {
-    cplx r;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-}
 
 struct Split {
     static constexpr int N = 1024, T = 8, M = 64, R3 = 4;
@@ -115,7 +110,7 @@ __device__ __forceinline__ void dit2048_tile(const cplx *__restrict__ src, long 
     for (int h = 0; h < 2; h++) {
         cplx v[16];
 #pragma unroll
-        for (int e = 0; e < 16; e++) v[e] = ld_stream2(&src[base + (long long) (2 * (b + M * e) + h) * nstride]);
+        for (int e = 0; e < 16; e++) v[e] = ld_stream(&src[base + (long long) (2 * (b + M * e) + h) * nstride]);
         __syncthreads();  // the image of the previous transform is no longer read
         const int bo = fft1024_split(v, S_pencil, b, tw, 2);  // v[e] = E[bo + 64 e] or O[bo + 64 e]: the same slot permutation
         if (h == 0) {
@@ -191,6 +186,121 @@ __global__ void __launch_bounds__(512, 1)
 
 constexpr size_t DIT_SMEM = Split::IMAGE_BYTES + Split::PARK_BYTES;
 
+// ------------------------------------------------------------------ y pass + emission at N = 2048
+// The y pass of the north-star size with 8-pencil tiles (128-byte runs on the loads, whole 32-byte sectors on the record
+// stores) instead of the 4-pencil tiles of fft_emit_strided_kernel<2048, 4>: the decimation transform above, whose two
+// outputs per butterfly (rows y and y + 1024) go straight into the record logic of fft_emit_*_kernel
+// (zplt_fft_kernels.cu; reference WriteParticlesSlab, src/output.cpp:41-234).  RVZel records only (BASELINE configs[3]
+// and [4]); the other formats keep the 4-pencil kernel.  One inlined copy of the transform inside a non-unrolled loop
+// over the packed arrays (A0, A2, A1, A3: the two parked floats first, then the two record halves), the array index is
+// CTA-uniform.  Persistent CTAs over (plane, x tile); parked fields live in an L2-resident area indexed by CTA.
+//   per CTA: keep0 [32][512] float (displ[2]) | keep1 [32][512] float (vel[2]) | d01 [32][512] float2 (displ[0], displ[1])
+#define ZPLT_EMIT2048_SLOT_BYTES (262144)
+__global__ void __launch_bounds__(512, 1)
+   fft2048_emit_kernel(const cplx *__restrict__ planes, long long z_first, long long nz, const __grid_constant__ EmitParams ep,
+                       const cplx *__restrict__ tw, unsigned int *__restrict__ counter) {
+    extern __shared__ __align__(16) unsigned char smem_dit[];
+    __shared__ double s_red[32][8];
+    __shared__ unsigned int s_next;
+    double *S  = reinterpret_cast<double *>(smem_dit);
+    cplx *park = reinterpret_cast<cplx *>(smem_dit + Split::IMAGE_BYTES);
+    constexpr int N = 2048, T = Split::T, XT = N / T, NT = Split::NT;
+    const int tid = threadIdx.x, p = tid % T, b = tid / T;
+    // this thread's parking column: keep0 = kp, keep1 = kp + 32*NT floats, d01 = the float2 area behind them
+    float *kp = reinterpret_cast<float *>(static_cast<unsigned char *>(ep.scratch) + (size_t) blockIdx.x * ZPLT_EMIT2048_SLOT_BYTES) + tid;
+#define keep0 kp
+#define keep1 (kp + 32 * NT)
+#define d01 (reinterpret_cast<float2 *>(kp + 64 * NT - tid) + tid)
+    const uint64_t pol = l2_evict_last();
+    const bool qplt = ep.qPLT;
+#define vn ep.vnorm
+    const int nsteps = qplt ? 4 : 2;
+    const unsigned int ntiles = (unsigned int) (XT * nz);
+    for (int i = tid; i < 32 * 8; i += NT) (&s_red[0][0])[i] = 0.0;
+    if (tid == 0) s_next = atomicAdd(counter, 1u);
+    __syncthreads();
+    unsigned int cur = s_next;
+    while (cur < ntiles) {
+        __syncthreads();  // everybody has read s_next
+        if (tid == 0) s_next = atomicAdd(counter, 1u);
+        const int x        = (int) (cur % XT) * T + p;
+        const long long zl = z_first + cur / XT;
+        const long long z  = zl + ep.zglobal0;
+        const cplx *src    = planes + zl * ep.zstride + x;
+        unsigned char *rec0 = ep.out + ((size_t) ((zl - ep.z0) * N) * N + x) * 32;
+        const unsigned int w1 = (unsigned int) (unsigned short) x;
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            const int A = qplt ? ((s == 0) ? 0 : (s == 1) ? 2 : (s == 2) ? 1 : 3) : s;
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;  // A0: sum dens^2, +max, -max of pos[0]; A1: +-max of pos[1], pos[2]
+            int j = 0;                                      // parking index of this butterfly's two values
+            dit2048_tile(src + (long long) A * ep.astride, 0, N, S + p * Split::PSTRIDE, park, tw, tid, b, [&](int k, cplx lo, cplx hi) {
+                const int jl = j * NT, jh = (j + 1) * NT;
+                j += 2;
+                if (A == 0) {  // Re = density, Im = pos[0] -> displ[2] (and vel[2] without qPLT): parked
+                    q0 += lo.x * lo.x + hi.x * hi.x;
+                    q1 = fmax(q1, fmax(lo.y, hi.y)), q2 = fmax(q2, fmax(-lo.y, -hi.y));
+                    if (ep.dens != nullptr) {
+                        float *dens0 = ep.dens + ((size_t) (zl - ep.z0) * N) * N + x;
+                        dens0[(size_t) k * N] = (float) lo.x, dens0[(size_t) (k + 1024) * N] = (float) hi.x;
+                    }
+                    if (ep.out != nullptr) {
+                        park_st<true>(keep0 + jl, (float) lo.y, pol), park_st<true>(keep0 + jh, (float) hi.y, pol);
+                        if (!qplt) park_st<true>(keep1 + jl, (float) (lo.y * vn), pol), park_st<true>(keep1 + jh, (float) (hi.y * vn), pol);
+                    }
+                } else if (A == 2) {  // Im = vel[0] -> vel[2]: parked
+                    if (ep.out != nullptr) park_st<true>(keep1 + jl, (float) lo.y, pol), park_st<true>(keep1 + jh, (float) hi.y, pol);
+                } else if (A == 1) {  // Re = pos[1] -> displ[1], Im = pos[2] -> displ[0]
+                    q0 = fmax(q0, fmax(lo.x, hi.x)), q1 = fmax(q1, fmax(-lo.x, -hi.x));
+                    q2 = fmax(q2, fmax(lo.y, hi.y)), q3 = fmax(q3, fmax(-lo.y, -hi.y));
+                    if (ep.out == nullptr) {
+                    } else if (qplt) {
+                        park_st2(d01 + jl, make_float2((float) lo.y, (float) lo.x), pol);
+                        park_st2(d01 + jh, make_float2((float) hi.y, (float) hi.x), pol);
+                    } else {
+                        const unsigned int wl = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) k << 16);
+                        const unsigned int wh = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) (k + 1024) << 16);
+                        st_record32(rec0 + (size_t) k * N * 32, make_float4(__uint_as_float(wl), __uint_as_float(w1), (float) lo.y, (float) lo.x),
+                                    make_float4(park_ld<true>(keep0 + jl, pol), (float) (lo.y * vn), (float) (lo.x * vn), park_ld<true>(keep1 + jl, pol)));
+                        st_record32(rec0 + (size_t) (k + 1024) * N * 32, make_float4(__uint_as_float(wh), __uint_as_float(w1), (float) hi.y, (float) hi.x),
+                                    make_float4(park_ld<true>(keep0 + jh, pol), (float) (hi.y * vn), (float) (hi.x * vn), park_ld<true>(keep1 + jh, pol)));
+                    }
+                } else if (ep.out != nullptr) {  // A == 3: Re = vel[1], Im = vel[2] -> vel[0]: the record is complete
+                    const float2 dl = park_ld2(d01 + jl, pol), dh = park_ld2(d01 + jh, pol);
+                    const unsigned int wl = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) k << 16);
+                    const unsigned int wh = (unsigned int) (unsigned short) z | ((unsigned int) (unsigned short) (k + 1024) << 16);
+                    st_record32(rec0 + (size_t) k * N * 32, make_float4(__uint_as_float(wl), __uint_as_float(w1), dl.x, dl.y),
+                                make_float4(park_ld<true>(keep0 + jl, pol), (float) lo.y, (float) lo.x, park_ld<true>(keep1 + jl, pol)));
+                    st_record32(rec0 + (size_t) (k + 1024) * N * 32, make_float4(__uint_as_float(wh), __uint_as_float(w1), dh.x, dh.y),
+                                make_float4(park_ld<true>(keep0 + jh, pol), (float) hi.y, (float) hi.x, park_ld<true>(keep1 + jh, pol)));
+                }
+            });
+            if (A == 0) {
+                fold_stats<NT, true>(s_red, tid, q0, 0, q1, 1, q2, 4);
+            } else if (A == 1) {
+                fold_stats<NT, true>(s_red, tid, q0, 2, q1, 5, q2, 3);
+                fold_stats<NT, true>(s_red, tid, q3, 6, 0.0, 7, 0.0, 7);
+            }
+        }
+        cur = s_next;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        constexpr int NW = NT / 32;
+        double a7 = s_red[0][tid];
+        for (int w = 1; w < NW; w++) a7 = (tid == 0) ? a7 + s_red[w][tid] : fmax(a7, s_red[w][tid]);
+        double *sl = ep.stats + 8 * (blockIdx.x % ZPLT_STAT_SLOTS);
+        if (tid == 0)
+            atomicAdd(&sl[0], a7);
+        else
+            atomicMax(reinterpret_cast<unsigned long long *>(&sl[tid]), (unsigned long long) __double_as_longlong(a7));
+    }
+#undef keep0
+#undef keep1
+#undef d01
+#undef vn
+}
+
 }  // namespace
 
 // In-place strided pass with the N = 2048 decimation kernel when it is enabled and the geometry is the 4-pencil
@@ -224,6 +334,24 @@ int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, c
         return (int) cudaGetLastError();
     }
     return launch_fft_tiles_p2p(N, T, b1, sg, peer_recv, tw, tn, lr, st);
+}
+
+// y pass + emission of planes [z_first, z_first + nz) with the 8-pencil decimation kernel; returns -1 when this launch
+// is not its case (then the caller uses the regular kernels)
+int launch_fft2048_emit(const cplx *planes, long long z_first, long long nz, const EmitParams &ep, const cplx *tw, const Tuning &tn,
+                        LaunchRes &lr, cudaStream_t st) {
+    if (tn.dit2048_emit <= 0 || ep.icformat != 1 || ep.astride == 0 || ep.scratch == nullptr || !lr.counters) return -1;
+    if (ep.out != nullptr && (reinterpret_cast<size_t>(ep.out) & 31)) return -1;  // 256-bit record stores
+    const long long ntiles = (long long) (2048 / 8) * nz;
+    if (ntiles >= (1ll << 31)) return -1;
+    long long nctas = ntiles < lr.sms ? ntiles : lr.sms;
+    if ((size_t) nctas * ZPLT_EMIT2048_SLOT_BYTES > ZPLT_SCRATCH_BYTES) nctas = ZPLT_SCRATCH_BYTES / ZPLT_EMIT2048_SLOT_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(fft2048_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DIT_SMEM);
+    if (e != cudaSuccess) return (int) e;
+    unsigned int *ctr = lr.counters + (lr.next_counter++ & 63);
+    if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return (int) cudaErrorMemoryAllocation;
+    fft2048_emit_kernel<<<(unsigned) nctas, 512, DIT_SMEM, st>>>(planes, z_first, nz, ep, tw, ctr);
+    return (int) cudaGetLastError();
 }
 
 }  // namespace zplt

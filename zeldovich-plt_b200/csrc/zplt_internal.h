@@ -55,7 +55,8 @@ struct Tuning {
     int emit_prefetch = 1;  // ZPLT_EMIT_PREFETCH: L2-prefetch the next packed array of a tile (one-tile-per-CTA kernel)
     int slab_groups  = 8;   // ZPLT_SLAB_GROUPS: row groups of stage 1 on a slab rank (generation of group j+1 overlaps the z pass of j)
     int p2p_ctas     = 96;  // ZPLT_P2P_CTAS: CTAs of the z pass + exchange kernel (0 = as many as fit)
-    int dit2048      = 0;   // ZPLT_DIT2048: 8-pencil decimation kernels for the N = 2048 strided passes
+    int dit2048      = 1;   // ZPLT_DIT2048: 8-pencil decimation kernels for the N = 2048 z pass (122 -> 77 ms per rank of 8, local stores)
+    int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
     int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
 };
@@ -86,6 +87,9 @@ int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx 
 int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st);
 int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
                              const Tuning &tn, LaunchRes &lr, cudaStream_t st);
+// N = 2048 y pass + emission with 8-pencil tiles (zplt_fft2048_kernels.cu); -1 = not applicable to this launch
+int launch_fft2048_emit(const cplx *planes, long long z_first, long long nz, const EmitParams &ep, const cplx *tw, const Tuning &tn,
+                        LaunchRes &lr, cudaStream_t st);
 // y-axis FFT fused with record emission (cube: x and z already transformed; not modified).
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
                             const EmitParams &ep, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st, int *launches);

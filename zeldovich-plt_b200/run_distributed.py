@@ -143,6 +143,8 @@ def main():
                   file=sys.stderr)
         print(f"zeldovich took {t2 - t0:.4g} sec for ppd {N} on {world} GPUs ==> {N**3 / 1e6 / (t2 - t0):.3g} Mpart/sec "
               f"(device {t1 - t0:.3g} s, writing {t2 - t1:.3g} s)", file=sys.stderr)
+    if world > 1 and args.exchange == "p2p":
+        ex.close()
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
