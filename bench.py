@@ -392,6 +392,7 @@ class Problem:
             from __graft_entry__ import load_synth
 
             synth = load_synth()
+            zo.set_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1 for its ranks; the other ranks only wait here
             k, p = synth.make_power_table()
             kw = dict(ppd=N, icformat=self.ctx.cfg.icformat)
             if self.qplt:

@@ -60,6 +60,15 @@ static inline uint64_t zo_next(u128 *state) {
     return (x >> rot) | (x << ((64 - rot) & 63));
 }
 
+/* worker threads of the OpenMP loops below (a launcher such as torchrun sets OMP_NUM_THREADS=1 for its ranks) */
+void zo_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void) n;
+#endif
+}
+
 /* n raw 64-bit outputs starting `offset` (= off_hi*2^64 + off_lo) draws after seeding */
 void zo_pcg_draws(uint64_t seed, uint64_t off_hi, uint64_t off_lo, int64_t n, uint64_t *out) {
     u128 s = zo_jump(zo_seed_state(seed), ZO_MAKE128(off_hi, off_lo));

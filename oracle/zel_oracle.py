@@ -124,6 +124,11 @@ def _eig(eig):
     return int(ppd_e), np.ascontiguousarray(tab, dtype=np.float64).reshape(-1)
 
 
+def set_threads(n):
+    """OpenMP threads of the oracle (torchrun pins its ranks to OMP_NUM_THREADS=1)."""
+    lib().zo_set_threads(int(n))
+
+
 def pcg_draws(seed, offset, n):
     out = np.empty(n, dtype=np.uint64)
     seed &= (1 << 64) - 1

@@ -117,12 +117,21 @@ def main():
         var = sum(p[1]["density_variance"] for p in parts)
         ref_ctx = make(0, 1)
         ref_ctx.generate()
-        want = ref_ctx.fetch_planes(0, N).view(np.uint8)
+        wantr = ref_ctx.fetch_planes(0, N)
+        want = wantr.view(np.uint8)
         rst = ref_ctx.stats()
         same = np.array_equal(got, want)
-        print(f"slab run PPD={N} world={world} p2p={args.p2p}: records identical to single-GPU run: {same}; "
+        # the z pass of a slab rank is another instantiation of the same transform (different FMA contraction choices by the
+        # compiler): ids must be identical, fields may differ in the last bit of a double, i.e. rarely by one float32 ulp
+        gotr = got.view(wantr.dtype)
+        ids = np.array_equal(gotr["ijk"], wantr["ijk"])
+        worst, ndiff = 0.0, int((gotr["displ"] != wantr["displ"]).sum() + (gotr["vel"] != wantr["vel"]).sum())
+        for f in ("displ", "vel"):
+            worst = max(worst, float(np.abs(gotr[f].astype(np.float64) - wantr[f].astype(np.float64)).max() / np.abs(wantr[f]).max()))
+        print(f"slab run PPD={N} world={world} p2p={args.p2p}: records byte-identical to single-GPU run: {same}; ids identical: {ids}; "
+              f"{ndiff} of {6 * N**3} float32 fields differ, worst {worst:.2e} of the field scale; "
               f"density variance {var:.12g} vs {rst['density_variance']:.12g}")
-        assert same
+        assert ids and worst < 2e-7
     dist.barrier()
     dist.destroy_process_group()
 

@@ -554,10 +554,14 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         // Slab rank with mapped peers: stage 1 runs in groups of rows.  The z pass of group j (NVLink-bound,
         // on the high-priority exchange stream) overlaps with the generation + x pass of group j+1.
         if (!gt) return fail(ZPLT_EINVAL, "no fused generation kernel for this size");
-        int J = c->tn.slab_groups;  // measured on 2 GPUs at PPD=1024: 1 group 69.4 ms/step, 4 groups 61.6, 8 groups + 96 CTAs 57.4
+        int J = c->tn.slab_groups;  // measured on 2 GPUs at PPD=1024 (whole step): 1 group 69.4 ms, 4 groups 54.8, 8 groups 53.5, 16 groups 53.0
         if (J < 1) J = 1;
         if (J > 16) J = 16;
         while (J > 1 && (c->sg.h % J)) J--;
+        // The two kernels share the SMs: the z pass is capped (Tuning::p2p_ctas CTAs, each fills an SM) at what keeps the
+        // links busy, generation takes the rest.  Measured on 2 GPUs at PPD=1024 (stage 1): 96 CTAs 42.5 ms, 64 CTAs 37.2 ms,
+        // uncapped 50.5 ms — with a static split stage 1 ~ max(z SM-time * 148/n, link time, gen SM-time * 148/(148-n)).
+        // The z pass of the last group has no generation left to share with and takes every SM.
         SlabGeom sg = c->sg;
         sg.nly      = c->sg.h / J;
         for (int j = 0; j < J; j++) {
@@ -565,7 +569,9 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
             CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->tn, c->lr, false, c->stream));
             CK(cudaEventRecord(c->ev_group[j], c->stream));
             CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[j], 0));
-            CK(launch_fft_tiles_p2p_any(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, c->tn, c->lr, c->xchg_stream));
+            Tuning tn = c->tn;
+            if (j == J - 1) tn.p2p_ctas = 0;
+            CK(launch_fft_tiles_p2p_any(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, tn, c->lr, c->xchg_stream));
         }
         c->launches[0] = J;
         c->launches[1] = J;

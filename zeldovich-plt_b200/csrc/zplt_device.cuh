@@ -295,9 +295,10 @@ __device__ __forceinline__ RowConst row_const(const GenParams &g, int y, int z) 
     return rc;
 }
 
+// xj0 = g.xjump[x0], loaded by the caller ahead of time (its latency hides behind the row's mask test)
 template <int RUN>
-__device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &rc, int x0, double (&Dr)[RUN], double (&Di)[RUN],
-                                            double (&s0)[RUN], double (&s1)[RUN], double (&s2)[RUN], double (&ff)[RUN]) {
+__device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &rc, int x0, const Affine &xj0, double (&Dr)[RUN],
+                                            double (&Di)[RUN], double (&s0)[RUN], double (&s1)[RUN], double (&s2)[RUN], double (&ff)[RUN]) {
     const int N = g.N, half = g.half, ky = rc.ky, kz = rc.kz;
     int kx[RUN], n2[RUN];
     bool act[RUN], any = false;
@@ -324,9 +325,11 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
     // the draws: masked sites consume theirs too, so the run is one walk of the generator.  The only
     // break is between x = N/2 (kx = +N/2) and x = N/2+1 (kx = -N/2+1); runs are aligned, so it can
     // only sit between the first and the second site of a run.
-    double u1[RUN], u2[RUN];
+    double u1[RUN], u2[RUN], Pk[RUN];
+#pragma unroll
+    for (int j = 0; j < RUN; j++) Pk[j] = __ldg(&g.ptab[n2[j]]);  // issued before the generator arithmetic that hides their latency
     {
-        u128 s = apply(g.xjump[x0], rc.s_yz);
+        u128 s = apply(xj0, rc.s_yz);
 #pragma unroll
         for (int j = 0; j < RUN; j++) {
             if (j == 1 && x0 == half) s = apply(g.xjump[x0 + 1], rc.s_yz);
@@ -340,7 +343,7 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
         }
     }
 #pragma unroll
-    for (int j = 0; j < RUN; j++) box_muller(g, __ldg(&g.ptab[n2[j]]), u1[j], u2[j], Dr[j], Di[j]);
+    for (int j = 0; j < RUN; j++) box_muller(g, Pk[j], u1[j], u2[j], Dr[j], Di[j]);
     }  // draws
 
     if (!g.qPLT) {

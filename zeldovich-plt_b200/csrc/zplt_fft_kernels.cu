@@ -155,6 +155,15 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
     constexpr int RUN = N / NT;  // = 16 / NP
     static_assert(RUN * NT == N && (RUN == 2 || RUN == 4 || RUN == 8), "whole runs");
 
+    // the row's generator state and this thread's jump along x: dependent table loads (L2 latency) and two 128-bit
+    // multiply-adds, issued before the mask test so that they overlap with it
+    RowConst rc;
+    Affine xj0;
+    if (y < half) {
+        xj0 = g.xjump[tid * RUN];
+        rc  = row_const(g, y, z);
+    }
+
     // ---- rows without a single unmasked mode (outside the k_cutoff sphere: 1 - pi/4 of all rows; the Nyquist
     //      row) are zero in every packed array, and so are their transforms: store zeros, skip everything else ----
     {
@@ -187,10 +196,7 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
         for (int c = 0; c < 6; c++)
 #pragma unroll
             for (int j = 0; j < RUN; j++) q[c][j] = 0.0;
-        if (y < half) {
-            const RowConst rc = row_const(g, y, z);
-            primary_run<RUN>(g, rc, tid * RUN, q[0], q[1], q[2], q[3], q[4], q[5]);
-        }
+        if (y < half) primary_run<RUN>(g, rc, tid * RUN, xj0, q[0], q[1], q[2], q[3], q[4], q[5]);
 #pragma unroll
         for (int c = 0; c < 6; c++)
 #pragma unroll
@@ -451,8 +457,8 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
     const double vn = ep.vnorm;
     b = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // from here on b is the OUTPUT slot
     const uint64_t pol = l2_evict_last();
-    // default (wide_records < 0): on in the persistent ring kernel, where it was measured (y pass 28.2 -> 24.9 ms at PPD=1024)
-    const bool wide    = (ep.wide_records > 0 || (ep.wide_records < 0 && ACC)) && (reinterpret_cast<size_t>(ep.out) & 31) == 0;
+    // default (wide_records < 0): on (measured in the persistent ring kernel: y pass 28.2 -> 24.9 ms at PPD=1024)
+    const bool wide    = ep.wide_records != 0 && (reinterpret_cast<size_t>(ep.out) & 31) == 0;
     double *keepd = reinterpret_cast<double *>(keep);  // the same 64 KB seen as [16][NT] doubles (non-RVZel formats)
     if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]: parked until A1 completes the displacement
         {
@@ -844,7 +850,7 @@ static int launch_tiles_ring_t(cplx *data, const TileGeom &g, const cplx *tw, La
 // sizes that have the ring-prefetched kernels instantiated (register file = one tile, shared memory = exchange image + ring)
 template <int N, int T>
 constexpr bool has_ring() {
-    return (N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32);
+    return (N == 2048 && T == 4) || (N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32);
 }
 
 template <int N, int T>

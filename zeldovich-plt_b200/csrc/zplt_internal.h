@@ -50,11 +50,11 @@ struct EmitParams {
 struct Tuning {
     int zring        = 12;  // ZPLT_ZRING: slices of the next tile the ring-prefetched strided pass requests through TMA (0 = plain kernel)
     int yring        = 12;  // ZPLT_YRING: the same for the y pass + emission (0 = one tile per CTA)
-    int wide_records = -1;  // ZPLT_WIDE_RECORDS: 256-bit RVZel record stores; -1 = where measured (ring kernels), 0 off, 1 on
+    int wide_records = -1;  // ZPLT_WIDE_RECORDS: 256-bit RVZel record stores (qPLT records written whole from the parking areas); 0 = off
     int emit_scratch = 1;   // ZPLT_EMIT_SCRATCH: park record halves in the L2-resident scratch (whole-record stores)
     int emit_prefetch = 1;  // ZPLT_EMIT_PREFETCH: L2-prefetch the next packed array of a tile (one-tile-per-CTA kernel)
-    int slab_groups  = 8;   // ZPLT_SLAB_GROUPS: row groups of stage 1 on a slab rank (generation of group j+1 overlaps the z pass of j)
-    int p2p_ctas     = 96;  // ZPLT_P2P_CTAS: CTAs of the z pass + exchange kernel (0 = as many as fit)
+    int slab_groups  = 16;  // ZPLT_SLAB_GROUPS: row groups of stage 1 on a slab rank (generation of group j+1 overlaps the z pass of j)
+    int p2p_ctas     = 64;  // ZPLT_P2P_CTAS: CTAs of the z pass + exchange kernel (0 = as many as fit); the last row group is not capped
     int dit2048      = 1;   // ZPLT_DIT2048: 8-pencil decimation kernels for the N = 2048 z pass (122 -> 77 ms per rank of 8, local stores)
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
