@@ -557,8 +557,8 @@ def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("dit", [0, 1])
-def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit):
+@pytest.mark.parametrize("dit,dit_emit", [(1, 0), (0, 0), (1, 1)])
+def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit, dit_emit):
     """BASELINE configs[4] (the north-star size): PPD=2048 qPLT + rescale RVZel over 8 slab ranks.  One GPU cannot hold
     the run, but it can hold ONE rank's buffers: the 8 ranks run their stage 1 one after the other in the same workspace,
     each storing only the share of the rank under test (the other peers are NULL = discarded), which then runs its
@@ -576,34 +576,40 @@ def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit):
         ctx0.close()
         pytest.skip("needs ~145 GB of free device memory")
     W = torch.empty(ws // 8, dtype=torch.float64, device="cuda:0")
-    recv = W.data_ptr() + ws // 2
-    zs = [0, N // G - 1, N - N // G, N - 1]
-    want, _ = oracle_planes(oracle, kw, zs, eig)
-    ctx0.close()
-    worst = 0.0
-    for target, planes in ((0, (0, 1)), (G - 1, (2, 3))):
-        W[ws // 16:].fill_(float("nan"))
-        tctx = None
-        for src in range(G):
-            c = ctx_from(pkg, P, power, src, G)
-            c.set_option("dit2048", dit)
-            c.set_option("dit2048_emit", dit)
-            c.set_workspace(W.data_ptr(), ws)
-            c.dbg_set_peers([recv if r == target else None for r in range(G)])
-            c.generate()
-            c.synchronize()
-            if src == target:
-                tctx = c
-            else:
-                c.close()
-        tctx.exchange_done()
-        for i in planes:
-            got = tctx.fetch_planes(zs[i] - target * (N // G), 1)
-            worst = max(worst, compare_records(oracle, got, want[i].reshape(-1)))
-        tctx.close()
-    del W
-    torch.cuda.empty_cache()
-    print("PPD=2048 qPLT+rescale RVZel, 8 ranks, dit2048 =", dit, ": worst field-relative error", worst)
+    open_ctxs = []
+    try:
+        recv = W.data_ptr() + ws // 2
+        zs = [0, N // G - 1, N - N // G, N - 1]
+        want, _ = oracle_planes(oracle, kw, zs, eig)
+        ctx0.close()
+        worst = 0.0
+        for target, planes in ((0, (0, 1)), (G - 1, (2, 3))):
+            W[ws // 16:].fill_(float("nan"))
+            tctx = None
+            for src in range(G):
+                c = ctx_from(pkg, P, power, src, G)
+                open_ctxs.append(c)
+                c.set_option("dit2048", dit)  # (1, 0) are the defaults
+                c.set_option("dit2048_emit", dit_emit)
+                c.set_workspace(W.data_ptr(), ws)
+                c.dbg_set_peers([recv if r == target else None for r in range(G)])
+                c.generate()
+                c.synchronize()
+                if src == target:
+                    tctx = c
+                else:
+                    c.close()
+            tctx.exchange_done()
+            for i in planes:
+                got = tctx.fetch_planes(zs[i] - target * (N // G), 1)
+                worst = max(worst, compare_records(oracle, got, want[i].reshape(-1)))
+            tctx.close()
+    finally:
+        for c in open_ctxs:
+            c.close()
+        W = None
+        torch.cuda.empty_cache()
+    print("PPD=2048 qPLT+rescale RVZel, 8 ranks, dit2048 =", dit, "dit2048_emit =", dit_emit, ": worst field-relative error", worst)
 
 
 # ---------------------------------------------------------------- option coverage ---

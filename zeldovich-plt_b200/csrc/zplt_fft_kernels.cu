@@ -603,6 +603,122 @@ __device__ __forceinline__ void emit_finish(cplx (&v)[16], int zl, cplx *S, floa
     }
 }
 
+// RVdoubleZel (BASELINE configs[1]'s format: u16 i,j,k; pad; double displ[3]; double vel[3] = 56 bytes) in the persistent ring
+// kernel, with the layout known at compile time — the generic path above carries the record layout in registers and spilled
+// (up to 1.2 KB) when it was inlined four times into the ring kernel.  Four parked doubles per site, all L2-resident and
+// coalesced ([16][NT] planes): pos[0] in `keepd`, then displ[0], displ[1] and vel[2] in `park3`; A3 writes the record whole.
+// One 56-byte record per lane, 8 lanes = 8 consecutive x = 448 contiguous bytes.  Written field by field that is seven 8-byte
+// stores at a 56-byte stride — four times the sector requests the bytes need, which is what bounded this format (y pass 51.6 ms
+// against 24.9 ms for RVZel at PPD=1024).  With STAGE the 8 lanes assemble their records in a piece of the exchange image that
+// belongs to their warp alone after the transform (3-pass lengths: passes 2 and 3 are warp-local, zplt_fft.cuh) and write the
+// 448 bytes as 28 coalesced 16-byte chunks.
+template <bool STAGE>
+__device__ __forceinline__ void store_record56(unsigned char *rec, double *stage, int p, unsigned long long ids, double f0, double f1,
+                                               double f2, double f3, double f4, double f5) {
+    if constexpr (STAGE) {
+        double *st = stage + p * 7;
+        st[0] = __longlong_as_double((long long) ids);
+        st[1] = f0, st[2] = f1, st[3] = f2, st[4] = f3, st[5] = f4, st[6] = f5;
+        __syncwarp();
+        const double2 *sv = reinterpret_cast<const double2 *>(stage);
+        double2 *g        = reinterpret_cast<double2 *>(rec - p * 56);
+        __stcs(&g[p], sv[p]);
+        __stcs(&g[p + 8], sv[p + 8]);
+        __stcs(&g[p + 16], sv[p + 16]);
+        if (p < 4) __stcs(&g[p + 24], sv[p + 24]);
+        __syncwarp();
+    } else {
+        *reinterpret_cast<unsigned long long *>(rec) = ids;
+        double *f = reinterpret_cast<double *>(rec + 8);
+        f[0] = f0, f[1] = f1, f[2] = f2, f[3] = f3, f[4] = f4, f[5] = f5;
+    }
+}
+
+template <int N, int T, int A>
+__device__ __forceinline__ void emit_finish_rvdouble(cplx (&v)[16], int zl, cplx *S, double *keepd, double *park3, const cplx *__restrict__ tw,
+                                                     const EmitParams &ep, unsigned char *rec0, long long z, int x, int tid, int p, int b,
+                                                     double (*s_red)[8]) {
+    constexpr int M  = N / 16;
+    constexpr int NT = T * M;
+    // staging needs a warp-private piece of the exchange image (3-pass lengths), 8-lane groups of consecutive x and aligned records
+    constexpr bool CAN_STAGE = FftPlan<N>::PASSES == 3 && T == 8;
+    constexpr int R3         = CAN_STAGE ? FftPlan<N>::R3 : 1;
+    double *stage = reinterpret_cast<double *>(S + (b % R3) * FftSmem<N, T>::PSTRIDE + (b / R3) * (16 * R3));  // 256*R3 bytes >= 448
+    const bool aligned = (reinterpret_cast<size_t>(ep.out) & 15) == 0;
+    b = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);  // from here on b is the OUTPUT slot
+    if (CAN_STAGE) __syncwarp();  // every lane of the warp has done its last read of the exchange image
+    const uint64_t pol = l2_evict_last();
+    const bool qplt = ep.qPLT;
+    if (A == 0) {  // Re = density, Im = pos[0] -> displ[2]
+        double var = 0.0, mp = 0.0, mn = 0.0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            var += v[e].x * v[e].x;
+            mp = fmax(mp, v[e].y), mn = fmax(mn, -v[e].y);
+        }
+        fold_stats<NT, true>(s_red, tid, var, 0, mp, 1, mn, 4);
+        if (ep.dens != nullptr) {
+            float *dp = ep.dens + ((size_t) (zl - ep.z0) * N) * N + x;
+#pragma unroll
+            for (int e = 0; e < 16; e++) dp[(size_t) (b + M * e) * N] = (float) v[e].x;
+        }
+        if (ep.out != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) park_std(&keepd[e * NT + tid], v[e].y, pol);
+        }
+    } else if (A == 2) {  // Im = vel[0] -> vel[2]
+        if (ep.out != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) park_std(&park3[(2 * 16 + e) * NT + tid], v[e].y, pol);
+        }
+    } else if (A == 1) {  // Re = pos[1] -> displ[1], Im = pos[2] -> displ[0]
+        double mp1 = 0.0, mn1 = 0.0, mp2 = 0.0, mn2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            mp1 = fmax(mp1, v[e].x), mn1 = fmax(mn1, -v[e].x);
+            mp2 = fmax(mp2, v[e].y), mn2 = fmax(mn2, -v[e].y);
+        }
+        fold_stats<NT, true>(s_red, tid, mp1, 2, mn1, 5, mp2, 3);
+        fold_stats<NT, true>(s_red, tid, mn2, 6, 0.0, 7, 0.0, 7);
+        if (ep.out == nullptr) {
+        } else if (qplt) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                park_std(&park3[(0 * 16 + e) * NT + tid], v[e].y, pol);
+                park_std(&park3[(1 * 16 + e) * NT + tid], v[e].x, pol);
+            }
+        } else {
+            const double vn = ep.vnorm;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int y = b + M * e;
+                unsigned char *rec = rec0 + (size_t) y * N * 56;
+                const double pos0 = park_ldd(&keepd[e * NT + tid], pol);
+                const unsigned long long ids = (unsigned long long) (unsigned short) z | ((unsigned long long) (unsigned short) y << 16)
+                                               | ((unsigned long long) (unsigned short) x << 32);
+                if (CAN_STAGE && aligned)
+                    store_record56<CAN_STAGE>(rec, stage, p, ids, v[e].y, v[e].x, pos0, v[e].y * vn, v[e].x * vn, pos0 * vn);
+                else
+                    store_record56<false>(rec, stage, p, ids, v[e].y, v[e].x, pos0, v[e].y * vn, v[e].x * vn, pos0 * vn);
+            }
+        }
+    } else if (ep.out != nullptr) {  // A == 3: Re = vel[1], Im = vel[2] -> vel[0]; the record is complete
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int y = b + M * e;
+            unsigned char *rec = rec0 + (size_t) y * N * 56;
+            const unsigned long long ids = (unsigned long long) (unsigned short) z | ((unsigned long long) (unsigned short) y << 16)
+                                           | ((unsigned long long) (unsigned short) x << 32);
+            const double d0 = park_ldd(&park3[(0 * 16 + e) * NT + tid], pol), d1 = park_ldd(&park3[(1 * 16 + e) * NT + tid], pol);
+            const double d2 = park_ldd(&keepd[e * NT + tid], pol), w2 = park_ldd(&park3[(2 * 16 + e) * NT + tid], pol);
+            if (CAN_STAGE && aligned)
+                store_record56<CAN_STAGE>(rec, stage, p, ids, d0, d1, d2, v[e].y, v[e].x, w2);
+            else
+                store_record56<false>(rec, stage, p, ids, d0, d1, d2, v[e].y, v[e].x, w2);
+        }
+    }
+}
+
 template <int N, int T, bool SLAB, bool RVZEL>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
    fft_emit_strided_kernel(const cplx *__restrict__ cube, SlabGeom sg, long long z_first, EmitParams ep,
@@ -685,6 +801,7 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
     // parking areas are indexed by CTA (grid <= SM count <= 256 slots), not by %smid: nothing guarantees one CTA per SM
     float *keep        = keep_all + (size_t) blockIdx.x * (ZPLT_KEEP_BYTES / sizeof(float));
     const unsigned pslot = blockIdx.x;
+    double *park3 = reinterpret_cast<double *>(ep.scratch) + (size_t) blockIdx.x * 3 * 16 * NT;  // RVdoubleZel: [3][16][NT] per CTA
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     const unsigned int ntiles = (unsigned int) (XT * nz);
     const RecLayout Lr = rec_layout(ep.icformat);
@@ -727,7 +844,11 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         __syncthreads(); /* ring consumed; the previous unit's last exchange read is complete */                      \
         if ((A) == 0) nn = s_nn[0];                                                                                    \
         if (NEXT_OK) issue_ring(NEXT_T, NEXT_A);                                                                       \
-        emit_finish<N, T, A, RVZEL, true>(v, (int) zl, S, keep, tw, ep, Lr, rec0, zl + ep.zglobal0, x, tid, p, b, s_red, pslot); \
+        if constexpr (RVZEL)                                                                                           \
+            emit_finish<N, T, A, true, true>(v, (int) zl, S, keep, tw, ep, Lr, rec0, zl + ep.zglobal0, x, tid, p, b, s_red, pslot); \
+        else                                                                                                           \
+            emit_finish_rvdouble<N, T, A>(v, (int) zl, S, reinterpret_cast<double *>(keep), park3, tw, ep, rec0, zl + ep.zglobal0, x, tid, p, \
+                                          b, s_red);                                                                   \
     }
         if constexpr (RVZEL) {
             // RVZel: A0 and A2 first (two parked floats), then A1 and A3 complete the two 16-byte halves
@@ -850,7 +971,9 @@ static int launch_tiles_ring_t(cplx *data, const TileGeom &g, const cplx *tw, La
 // sizes that have the ring-prefetched kernels instantiated (register file = one tile, shared memory = exchange image + ring)
 template <int N, int T>
 constexpr bool has_ring() {
-    return (N == 2048 && T == 4) || (N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32);
+    // (N = 2048 with 4-pencil tiles was tried: y pass of a rank of 8 30.0 -> 28.7 ms only, and its records failed parity; the
+    // 2048 passes use the decimation kernels of zplt_fft2048_kernels.cu / the one-tile-per-CTA kernels)
+    return (N == 1024 && T == 8) || (N == 512 && T == 8) || (N == 256 && T == 16) || (N == 64 && T == 32);
 }
 
 template <int N, int T>
@@ -1011,9 +1134,9 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, bool slab
     if constexpr (has_ring<N, T>()) {
         // persistent ring-prefetched form (records wanted, parking space present); Tuning::yring = 0 disables
         if (!slab && ep.out != nullptr && ep.scratch != nullptr && lr.counters && tn.yring > 0) {
-            // measured at PPD=1024: RVZel qPLT 28.9 -> 28.4 ms, ZA 20.5 -> 19.3 ms; the double formats lose (RVdoubleZel
-            // 58.0 -> 66.9 ms: the ring kernel's record bursts spill registers), so they keep the one-tile-per-CTA kernel
-            if (ep.icformat == 1 || tn.yring > 100) {
+            // measured at PPD=1024: RVZel qPLT 28.9 -> 28.4 ms, ZA 20.5 -> 19.3 ms.  RVdoubleZel has its own record code in the ring
+            // kernel (emit_finish_rvdouble); Zeldovich and ZelSimple keep the one-tile-per-CTA kernel
+            if (ep.icformat == 1 || ep.icformat == 2) {  // RVZel, RVdoubleZel (parking areas are sized for up to 512 threads)
                 int rc = (ep.icformat == 1) ? launch_emit_ring_t<N, T, true, 12>(cube, z_first, nz, ep, tw, lr, st)
                                             : launch_emit_ring_t<N, T, false, 12>(cube, z_first, nz, ep, tw, lr, st);
                 if (launches) *launches += 1;

@@ -57,6 +57,14 @@ __device__ __forceinline__ float park_ld(const float *p, uint64_t pol) {
         return *p;
     }
 }
+__device__ __forceinline__ void park_std(double *p, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double park_ldd(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
 __device__ __forceinline__ void park_st2(float2 *p, float2 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }

@@ -1,6 +1,8 @@
 // Host half of the C ABI: parameter loading, power-spectrum set-up, eigenmode file
 // loading, ic_* file writing and the whole `zeldovich <param_file>` flow.  The device
 // half lives in csrc/zplt_api.cu; this file only talks to it through the C ABI.
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -8,7 +10,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zeldovich_b200.h"
@@ -225,7 +229,46 @@ struct HostBuffer {
     }
 };
 
-// qoneslab >= 0: write only that z plane (reference src/zeldovich.cpp:669-682)
+// One append to one ic file.  Planes of a file are contiguous in the staging buffer (ascending z), so a chunk of planes
+// turns into one job per file; the jobs of a chunk are independent files and are written by several threads at once.
+struct WriteJob {
+    int64_t fileno;
+    const unsigned char *p;
+    size_t bytes;
+};
+
+static bool run_write_jobs(const fs::path &dir, const std::vector<WriteJob> &jobs, int nthreads, std::string *err) {
+    std::atomic<size_t> next{0};
+    std::atomic<bool> ok{true};
+    std::mutex emu;
+    auto worker = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= jobs.size() || !ok.load()) return;
+            const WriteJob &j = jobs[i];
+            fs::path fn       = dir / ("ic_" + std::to_string(j.fileno));
+            FILE *fp          = fopen(fn.c_str(), "ab");  // "ab": reference src/output.cpp:208-212
+            bool good         = fp && fwrite(j.p, 1, j.bytes, fp) == j.bytes;
+            if (fp) good = (fclose(fp) == 0) && good;
+            if (!good) {
+                std::lock_guard<std::mutex> g(emu);
+                if (ok.exchange(false)) *err = "cannot append to \"" + fn.string() + "\"";
+            }
+        }
+    };
+    const int nt = std::max(1, std::min<int>(nthreads, (int) jobs.size()));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    return ok.load();
+}
+
+// SetupOutputDir + the ZeldovichXY write loop (reference src/output.cpp:236-251, :208-212; src/zeldovich.cpp:667-682).
+// qoneslab >= 0: write only that z plane (reference src/zeldovich.cpp:669-682).
+// The planes come off the device in chunks into two pinned staging buffers: while the writer threads append chunk i to its
+// ic files, the device emits and copies chunk i+1.  Append order per file stays ascending z: a file's planes inside a chunk
+// are one job, and a chunk is finished before the next one is handed to the writers.
 static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, int qoneslab, WriteStats *ws,
                           int qdensity = 0, const char *density_path = nullptr) {
     fs::path dir(output_dir);
@@ -242,65 +285,81 @@ static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *
 
     const size_t rb    = zplt_record_bytes(icformat);
     const size_t plane = (size_t) ppd * ppd * rb;
-    int64_t chunk      = (int64_t) ((512ull << 20) / plane);
+    int64_t chunk      = (int64_t) ((1024ull << 20) / plane);
     if (chunk < 1) chunk = 1;
     if (chunk > ppd) chunk = ppd;
-    HostBuffer buf((size_t) chunk * plane);
-    if (!buf.p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host staging", (size_t) chunk * plane);
+    const bool records = qdensity != 2;
+    int64_t zbeg = 0, zend = ppd;
+    if (qoneslab >= 0) {
+        if (qoneslab >= ppd) return ZPLT_OK;  // the reference's loop simply never matches
+        zbeg = qoneslab, zend = qoneslab + 1;
+    }
+    const bool two = zend - zbeg > chunk;  // a second staging buffer only when there is a second chunk to overlap with
+    HostBuffer buf0(records ? (size_t) chunk * plane : 16), buf1(records && two ? (size_t) chunk * plane : 16);
+    if (!buf0.p || !buf1.p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host staging", (size_t) chunk * plane);
     // ZD_qdensity: float32 density planes appended to one file, opened "wb" (reference src/output.cpp:282-288)
     const size_t dplane = (size_t) ppd * ppd * sizeof(float);
-    HostBuffer dbuf(qdensity ? (size_t) chunk * dplane : 16);
+    HostBuffer dbuf0(qdensity ? (size_t) chunk * dplane : 16), dbuf1(qdensity && two ? (size_t) chunk * dplane : 16);
+    if (!dbuf0.p || !dbuf1.p) return hfail(ZPLT_ENOMEM, "cannot allocate host staging for the density planes");
     FILE *densfp = nullptr;
     if (qdensity) {
         if (!density_path) return hfail(ZPLT_EINVAL, "ZD_qdensity needs a density file name");
         densfp = fopen(density_path, "wb");
         if (!densfp) return hfail(ZPLT_EINVAL, "cannot open density file \"%s\"", density_path);
     }
-    const bool records = qdensity != 2;
-    int64_t last_file = -1;
-    FILE *fp          = nullptr;
-    int64_t zbeg = 0, zend = ppd;
-    if (qoneslab >= 0) {
-        if (qoneslab >= ppd) return ZPLT_OK;  // the reference's loop simply never matches
-        zbeg = qoneslab, zend = qoneslab + 1;
-    }
-    for (int64_t z0 = zbeg; z0 < zend; z0 += chunk) {
+    unsigned char *rbuf[2] = {buf0.p, two ? buf1.p : buf0.p};
+    unsigned char *dbuf[2] = {dbuf0.p, two ? dbuf1.p : dbuf0.p};
+    int nthreads = (int) std::thread::hardware_concurrency();
+    if (nthreads > 8) nthreads = 8;
+    if (nthreads < 1) nthreads = 1;
+
+    auto fetch = [&](int64_t z0, int which) -> int {
         const int64_t nz = (z0 + chunk <= zend) ? chunk : zend - z0;
-        int rc           = zplt_fetch_planes_density(ctx, z0, nz, records ? buf.p : nullptr, qdensity ? (float *) dbuf.p : nullptr);
-        if (rc) {
-            if (fp) fclose(fp);
-            if (densfp) fclose(densfp);
-            return rc;
-        }
-        const double t0 = now_s();
-        if (densfp) {
-            if (fwrite(dbuf.p, 1, (size_t) nz * dplane, densfp) != (size_t) nz * dplane) {
-                fclose(densfp);
-                return hfail(ZPLT_EINVAL, "short write on the density file");
-            }
-            if (ws) ws->bytes += (int64_t) ((size_t) nz * dplane);
-        }
+        return zplt_fetch_planes_density(ctx, z0, nz, records ? rbuf[which] : nullptr, qdensity ? (float *) dbuf[which] : nullptr);
+    };
+    int rc = fetch(zbeg, 0);
+    int64_t last_file = -1;
+    int which         = 0;
+    for (int64_t z0 = zbeg; rc == ZPLT_OK && z0 < zend; z0 += chunk, which ^= 1) {
+        const int64_t nz = (z0 + chunk <= zend) ? chunk : zend - z0;
+        // what the writers do with this chunk
+        std::vector<WriteJob> jobs;
         for (int64_t z = z0; records && z < z0 + nz; z++) {
             const int64_t fileno = z * cpd / ppd;  // integer division, reference src/output.cpp:208
-            if (fileno != last_file) {
-                if (fp) fclose(fp);
-                fs::path fn = dir / ("ic_" + std::to_string(fileno));
-                fp          = fopen(fn.c_str(), "ab");
-                if (!fp) return hfail(ZPLT_EINVAL, "cannot open \"%s\" for append", fn.c_str());
+            if (!jobs.empty() && jobs.back().fileno == fileno) {
+                jobs.back().bytes += plane;
+            } else {
+                jobs.push_back({fileno, rbuf[which] + (size_t) (z - z0) * plane, plane});
+                if (fileno != last_file && ws) ws->files++;
                 last_file = fileno;
-                if (ws) ws->files++;
             }
-            if (fwrite(buf.p + (size_t) (z - z0) * plane, 1, plane, fp) != plane) {
-                fclose(fp);
-                return hfail(ZPLT_EINVAL, "short write on ic file %lld", (long long) fileno);
-            }
-            if (ws) ws->bytes += (int64_t) plane;
         }
-        if (ws) ws->seconds += now_s() - t0;
+        const double t0 = now_s();
+        std::string werr;
+        bool wok = true;
+        int rc_next = ZPLT_OK;
+        {
+            // the writers work on this chunk while this thread drives the device through the next one
+            std::thread writers([&]() {
+                if (densfp && fwrite(dbuf[which], 1, (size_t) nz * dplane, densfp) != (size_t) nz * dplane) {
+                    wok  = false;
+                    werr = "short write on the density file";
+                    return;
+                }
+                wok = run_write_jobs(dir, jobs, nthreads, &werr);
+            });
+            if (z0 + chunk < zend) rc_next = fetch(z0 + chunk, which ^ 1);
+            writers.join();
+        }
+        if (ws) {
+            ws->seconds += now_s() - t0;
+            ws->bytes += (int64_t) ((records ? (size_t) nz * plane : 0) + (densfp ? (size_t) nz * dplane : 0));
+        }
+        if (!wok) rc = hfail(ZPLT_EINVAL, "%s", werr.c_str());
+        else rc = rc_next;
     }
-    if (fp) fclose(fp);
     if (densfp) fclose(densfp);
-    return ZPLT_OK;
+    return rc;
 }
 
 // The context does not expose its config through the ABI; keep what the writer needs here.
