@@ -61,7 +61,7 @@ typedef struct zplt_config {
     int32_t device;       /* CUDA device ordinal, or -1 for the current device */
     int32_t rank;         /* slab decomposition: this context's rank ... */
     int32_t nranks;       /* ... of nranks (1 = whole problem on this GPU) */
-    double f_NL;          /* ZD_f_NL: local primordial non-Gaussianity (0 = Gaussian); single GPU only */
+    double f_NL;          /* ZD_f_NL: local primordial non-Gaussianity (0 = Gaussian); on slab ranks see zplt_potential_begin */
     double n_s;           /* ZD_n_s: spectral index of the primordial power (only used with f_NL) */
     double Omega_M;       /* Omega_M at z = 0 (only used with f_NL) */
 } zplt_config;
@@ -152,6 +152,17 @@ int zplt_ipc_import(zplt_ctx *ctx, int32_t nranks, const void *handles);
 /* Unmap the peers' buffers again.  Every rank must have done so (barrier) before any rank frees its workspace or
  * destroys its context: freeing memory a peer still has mapped is undefined (CUDA IPC rule). */
 int zplt_ipc_close(zplt_ctx *ctx);
+/* ZD_f_NL != 0 on slab ranks with mapped peers: the potential pass (reference main, src/zeldovich.cpp:945-960) has two
+ * transposes of its own, so every step becomes
+ *     zplt_potential_begin      phi_g(k) = D/M on this rank's rows, x and z transforms, results stored into the owners' planes
+ *     [synchronise + barrier]
+ *     zplt_potential_exchange   y transform, phi_g + f_NL phi_g^2, y and x transforms, rows y < ppd/2 stored back to their owners
+ *     [synchronise + barrier]
+ *     zplt_generate             z transform of the returned rows, then the ordinary generation reading D = conj(phi) M
+ * (distributed.PeerExchange.generate does all of it).  The two potential buffers live behind the slab buffers in the
+ * workspace (zplt_workspace_bytes counts them). */
+int zplt_potential_begin(zplt_ctx *ctx);
+int zplt_potential_exchange(zplt_ctx *ctx);
 /* Layout of the decomposition (host mirror of the device index math, for tests and bindings):
  * which rank owns row y in stage 1 and in which of its slots. */
 int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32_t *slot);

@@ -503,6 +503,10 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     (8, {"slab_ring": 0, "yring": 0, "slab_groups": 3}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
     (2, {"slab_groups": 1, "p2p_ctas": 0}, dict(ppd=128, k_cutoff=2.0, icformat="Zeldovich")),
     (4, {}, dict(ppd=512, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    # ZD_f_NL on slab ranks: the potential pass with its own two exchanges (reference src/zeldovich.cpp:699-790, 945-960)
+    (2, {}, dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16, f_NL=2500.0, n_s=0.96, Omega_M=0.3)),
+    (4, {}, dict(ppd=128, icformat="RVdoubleZel", f_NL=-4000.0, n_s=0.97, Omega_M=0.31, k_cutoff=2.0)),
+    (8, {"slab_ring": 0}, dict(ppd=256, qPLT=1, icformat="RVZel", eig=256, f_NL=1000.0, n_s=0.96, Omega_M=0.3)),
 ])
 def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
     """The product's multi-GPU stage 1 on one GPU: every rank of a G-rank run executes the grouped, overlapped generation
@@ -519,7 +523,7 @@ def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
     ctx0, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig, rank=0, nranks=G)
     ctxs = [ctx0] + [ctx_from(pkg, P, power, r, G) for r in range(1, G)]
     bufs = [torch.empty(c.workspace_bytes() // 8, dtype=torch.float64, device="cuda:0") for c in ctxs]
-    half_bytes = ctxs[0].workspace_bytes() // 2
+    half_bytes = 16 * ctxs[0].narray * N**3 // G  # the receive buffer follows the stage-1 buffer
     for c, b in zip(ctxs, bufs):
         for k, v in opts.items():
             c.set_option(k, v)
@@ -527,6 +531,14 @@ def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
         b.fill_(float("nan"))  # every row of every receive buffer must be written by somebody
     for c in ctxs:
         c.dbg_set_peers([b.data_ptr() + half_bytes for b in bufs])
+    if kw.get("f_NL", 0.0) != 0.0:
+        # the potential pass of slab ranks: two more exchanges, a barrier (here: a device synchronisation) after each stage
+        for c in ctxs:
+            c.potential_begin()
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.potential_exchange()
+        torch.cuda.synchronize()
     for c in ctxs:
         c.generate()
     for c in ctxs:

@@ -94,7 +94,7 @@ EXPORTS = [
     "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_emit_planes_density", "zplt_fetch_planes_density",
     "zplt_write_outputs", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
     "zplt_get_timings", "zplt_set_option", "zplt_dbg_set_peers", "zplt_dbg_spectral_hot", "zplt_dbg_hot_draws", "zplt_dbg_fft_variant",
-    "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_ipc_close", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
+    "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_ipc_close", "zplt_potential_begin", "zplt_potential_exchange", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
     "zplt_power_sigmaR", "zplt_power_infer_Tk", "zplt_power_primordial_norm", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
@@ -142,6 +142,8 @@ def lib():
     L.zplt_ipc_export.argtypes = [vp, C.c_char_p]
     L.zplt_ipc_import.argtypes = [vp, i32, C.c_char_p]
     L.zplt_ipc_close.argtypes = [vp]
+    L.zplt_potential_begin.argtypes = [vp]
+    L.zplt_potential_exchange.argtypes = [vp]
     L.zplt_slab_owner.argtypes = [i64, i32, i64, C.POINTER(i32), C.POINTER(i32)]
     L.zplt_slab_offset.argtypes = [i64, i32, i32, i32, i32, i32, i64, i64]
     L.zplt_slab_offset.restype = i64
@@ -372,6 +374,14 @@ class Context:
         blob = b"".join(handles)
         assert len(blob) == 64 * len(handles)
         _ck(lib().zplt_ipc_import(self._h, len(handles), blob))
+
+    def potential_begin(self):
+        """ZD_f_NL on slab ranks, stage 1 of the potential pass (a barrier across ranks follows)."""
+        _ck(lib().zplt_potential_begin(self._h))
+
+    def potential_exchange(self):
+        """ZD_f_NL on slab ranks, stage 2 of the potential pass (a barrier across ranks follows, then generate())."""
+        _ck(lib().zplt_potential_exchange(self._h))
 
     def ipc_close(self):
         _ck(lib().zplt_ipc_close(self._h))

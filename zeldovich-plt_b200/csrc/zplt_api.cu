@@ -75,6 +75,8 @@ struct zplt_ctx {
     GenParams gp;
     SlabGeom sg;
     size_t slab_elems;  // complex elements of one slab buffer
+    size_t phi_elems;   // slab rank with ZD_f_NL: complex elements of one buffer of the potential pass (else 0)
+    int phi_stage;      // slab rank with ZD_f_NL: 0 = nothing, 1 = zplt_potential_begin done, 2 = zplt_potential_exchange done
     bool exchanged;
     bool p2p;               // peers' stage-2 buffers are mapped: the z pass stores straight into them
     bool dbg_peers;         // ... through zplt_dbg_set_peers (same-device buffers, tests) rather than CUDA IPC
@@ -201,8 +203,6 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(ZPLT_EINVAL, "bad rank %d of %d", cfg->rank, cfg->nranks);
     if (cfg->nranks > 1 && ((N / 2) % cfg->nranks || N / (2 * cfg->nranks) < 1))
         return fail(ZPLT_EINVAL, "nranks=%d must divide ppd/2=%lld", cfg->nranks, N / 2);
-    if (cfg->f_NL != 0. && cfg->nranks > 1)
-        return fail(ZPLT_EINVAL, "ZD_f_NL != 0 needs the whole potential on one GPU (nranks = 1)");
     if (cfg->f_NL != 0. && !(cfg->Omega_M > 0.)) return fail(ZPLT_EINVAL, "ZD_f_NL != 0 needs Omega_M > 0");
 
     int ndev = 0;
@@ -250,8 +250,11 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     while ((1 << c->sg.log2G) < c->sg.G) c->sg.log2G++;
     c->sg.ly0 = 0, c->sg.nly = c->sg.h;
     c->slab_elems = (size_t) c->na * N * N * N / cfg->nranks;
-    // one buffer on a single GPU; stage-1 + stage-2 buffers when the grid is slab-decomposed
-    c->cube_bytes = c->slab_elems * sizeof(cplx) * (cfg->nranks > 1 ? 2 : 1);
+    // one buffer on a single GPU; stage-1 + stage-2 buffers when the grid is slab-decomposed, followed — with ZD_f_NL — by the
+    // two buffers of the potential pass (this rank's rows [z][slot][x], this rank's planes [zl][y][x]), inside the same
+    // allocation so that one IPC handle maps everything a peer stores into
+    c->phi_elems  = (cfg->nranks > 1 && cfg->f_NL != 0.) ? (size_t) N * N * N / cfg->nranks : 0;
+    c->cube_bytes = (c->slab_elems * (cfg->nranks > 1 ? 2 : 1) + 2 * c->phi_elems) * sizeof(cplx);
 
     // derived scalars, written exactly as the reference computes them
     GenParams &g  = c->gp;
@@ -502,15 +505,103 @@ static int run_potential(zplt_ctx *c) {
     GenParams g = c->gp;
     g.phi       = nullptr;
     g.mtab      = c->mtab;
-    CK(launch_generate_phi(g, c->phi, c->stream));
+    CK(launch_generate_phi(g, c->sg, c->phi, c->stream));
     const int T = fft_tile_T(N);
     const int axes[3] = {0, 2, 1};
     for (int pass = 0; pass < 2; pass++) {
         for (int i = 0; i < 3; i++) CK(launch_fft_tiles_any(N, T, c->phi, geom_axis(N, 1, axes[i]), c->tw, c->tn, c->lr, c->stream));
-        if (pass == 0) CK(launch_fnl_local(c->phi, N, c->cfg.f_NL, c->stream));
+        if (pass == 0) CK(launch_fnl_local(c->phi, N, (long long) N * N * N, c->cfg.f_NL, c->stream));
     }
     c->gp.phi  = c->phi;
     c->gp.mtab = c->mtab;
+    c->gp.phi_zstride = (long long) N * N, c->gp.phi_yshift = 0;
+    return ZPLT_OK;
+}
+
+// ---- ZD_f_NL on slab ranks: the same pass with its two transposes (reference ZeldovichZ gen_phi + ZeldovichXY_Phi with
+// StoreBlock/LoadBlock and StoreBlockForward/LoadBlockForward, src/zeldovich.cpp:699-790, src/block_array.cpp:305-464) ----
+// buffers behind the two slab buffers: P1 = this rank's rows [z][slot][x], P2 = this rank's planes [zl][y][x]
+static cplx *phi_p1(zplt_ctx *c) { return c->cube + 2 * c->slab_elems; }
+static cplx *phi_p2(zplt_ctx *c) { return c->cube + 2 * c->slab_elems + c->phi_elems; }
+
+static TileGeom rows_geom(int N, int T, long long nrows_per_block, long long nblocks, long long block_stride) {
+    // contiguous rows of N points: nblocks blocks of nrows_per_block consecutive rows, block_stride elements apart
+    TileGeom g;
+    g.nstride = 1, g.plo_stride = N, g.phi_stride = 0, g.pa = T;
+    g.tstride = (long long) T * N, g.grid_x = (int) (nrows_per_block / T);
+    g.ostride = block_stride, g.grid_y = (int) nblocks;
+    g.astride = 0, g.grid_z = 1;
+    return g;
+}
+
+static int slab_potential_ready(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (c->sg.G == 1 || c->cfg.f_NL == 0.) return fail(ZPLT_EINVAL, "the staged potential pass belongs to slab ranks with ZD_f_NL != 0");
+    if (!c->p2p) return fail(ZPLT_ESTATE, "ZD_f_NL on slab ranks needs mapped peers (zplt_ipc_import)");
+    return ready(c);
+}
+
+// Stage 1 (rows): phi_g(k) = D/M on this rank's rows, x transform, z transform with the results stored into the owners' planes.
+extern "C" int zplt_potential_begin(zplt_ctx *c) {
+    int rc = slab_potential_ready(c);
+    if (rc) return rc;
+    const int N = c->N, T = fft_tile_T(N), h = c->sg.h;
+    if (!c->mtab) CK(cudaMalloc((void **) &c->mtab, c->ptab_count * sizeof(double)));
+    CK(launch_mfactor_table(c->mtab, c->ptab, c->ptab_count, c->gp.fundamental2, c->primordial_norm, c->cfg.n_s, c->cfg.z_initial,
+                            c->cfg.Omega_M, c->stream));
+    GenParams g = c->gp;
+    g.phi       = nullptr;
+    g.mtab      = c->mtab;
+    cplx *P1    = phi_p1(c);
+    CK(launch_generate_phi(g, c->sg, P1, c->stream));
+    CK(launch_fft_tiles_any(N, T, P1, rows_geom(N, T, (long long) N * 2 * h, 1, 0), c->tw, c->tn, c->lr, c->stream));
+    SlabGeom s1 = c->sg;
+    s1.na = 1, s1.ly0 = 0, s1.nly = h;
+    cplx *peers[16];
+    for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->slab_elems + c->phi_elems : nullptr;
+    Tuning tn   = c->tn;
+    tn.p2p_ctas = 0;  // nothing runs beside it
+    CK(launch_fft_tiles_p2p_any(N, T, P1, s1, peers, c->tw, tn, c->lr, c->stream));
+    c->phi_stage = 1;
+    return ZPLT_OK;
+}
+
+// Stage 2 (planes; after a barrier): y transform, phi_g + f_NL phi_g^2 in configuration space, y and x transforms of the real
+// result (its forward transform is the conjugate of its backward transform), rows y < N/2 back to their owners.
+extern "C" int zplt_potential_exchange(zplt_ctx *c) {
+    int rc = slab_potential_ready(c);
+    if (rc) return rc;
+    if (c->phi_stage != 1) return fail(ZPLT_ESTATE, "zplt_potential_begin (and a barrier across ranks) comes first");
+    const int N = c->N, T = fft_tile_T(N), np = N / c->sg.G;
+    cplx *P2 = phi_p2(c);
+    TileGeom gy;  // pencils along y of the planes [zl][y][x]
+    gy.nstride = N, gy.plo_stride = 1, gy.phi_stride = 0, gy.pa = T, gy.tstride = T, gy.grid_x = N / T;
+    gy.ostride = (long long) N * N, gy.grid_y = np, gy.astride = 0, gy.grid_z = 1;
+    CK(launch_fft_tiles_any(N, T, P2, gy, c->tw, c->tn, c->lr, c->stream));
+    CK(launch_fnl_local(P2, N, (long long) c->phi_elems, c->cfg.f_NL, c->stream));
+    CK(launch_fft_tiles_any(N, T, P2, gy, c->tw, c->tn, c->lr, c->stream));
+    // x transform of the rows that are read back: y < N/2 of every plane
+    CK(launch_fft_tiles_any(N, T, P2, rows_geom(N, T, N / 2, np, (long long) N * N), c->tw, c->tn, c->lr, c->stream));
+    cplx *peers[16];
+    for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->slab_elems : nullptr;
+    CK(launch_phi_return(P2, c->sg, peers, c->stream));
+    c->phi_stage = 2;
+    return ZPLT_OK;
+}
+
+// Stage 3 (rows; after a barrier, inside zplt_generate): z transform of the primary rows; the generation kernels read them.
+static int slab_potential_finish(zplt_ctx *c) {
+    if (c->phi_stage != 2)
+        return fail(ZPLT_ESTATE, "ZD_f_NL on slab ranks: zplt_potential_begin, barrier, zplt_potential_exchange, barrier come before zplt_generate");
+    const int N = c->N, T = fft_tile_T(N), h = c->sg.h;
+    cplx *P1 = phi_p1(c);
+    TileGeom gz;  // pencils along z of the rows [z][slot][x], primary slots only
+    gz.nstride = (long long) 2 * h * N, gz.plo_stride = 1, gz.phi_stride = 0, gz.pa = T, gz.tstride = T, gz.grid_x = N / T;
+    gz.ostride = N, gz.grid_y = h, gz.astride = 0, gz.grid_z = 1;
+    CK(launch_fft_tiles_any(N, T, P1, gz, c->tw, c->tn, c->lr, c->stream));
+    c->gp.phi = P1, c->gp.mtab = c->mtab;
+    c->gp.phi_zstride = (long long) 2 * h * N, c->gp.phi_yshift = c->sg.log2G;
+    c->phi_stage = 0;
     return ZPLT_OK;
 }
 
@@ -546,7 +637,7 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
     if (slab && !with_fft) return fail(ZPLT_EINVAL, "spectral introspection is single-GPU only");
     CK(cudaEventRecord(c->ev_gen[0], c->stream));
     if (c->cfg.f_NL != 0.) {
-        if ((rc = run_potential(c))) return rc;
+        if ((rc = slab ? slab_potential_finish(c) : run_potential(c))) return rc;
         c->launches[0] += 10;
     }
     const int gt = (with_fft || hot) ? gen_xfft_T(c->N, c->na) : 0;

@@ -89,6 +89,10 @@ struct GenParams {
     // the reference takes.  mtab[m] = M(k = sqrt(m) * fundamental), the potential -> density factor.
     const double2 *phi;
     const double *mtab;
+    // where row (z, y < N/2) of phi starts, in elements: z*phi_zstride + (y >> phi_yshift)*N.  Single GPU: the cube
+    // [z][y][x] (zstride N^2, shift 0).  Slab rank: its own rows [z][slot][x] (zstride 2h*N, slot = y / G).
+    long long phi_zstride;
+    int phi_yshift;
     // introspection of the hot kernel (parity tests): when non-NULL, primary_run stores the two raw 64-bit draws of every
     // site it walks at dbg_raw[((z*N/2 + y)*N + x)*2 ..] (rows it skips as all-masked stay untouched)
     unsigned long long *dbg_raw;
@@ -222,7 +226,7 @@ __device__ __forceinline__ void primary_mode(const GenParams &g, int x, int y, i
     m.Dr = m.Di = m.s0 = m.s1 = m.s2 = m.f = 0.0;
     if (g.phi != nullptr) {
         if (n2 == 0) return;
-        const double2 ph = g.phi[((size_t) z * g.N + y) * g.N + x];
+        const double2 ph = g.phi[(size_t) z * g.phi_zstride + (size_t) (y >> g.phi_yshift) * g.N + x];
         const double M   = __ldg(&g.mtab[n2]);
         m.Dr = ph.x * M, m.Di = -ph.y * M;
     } else {
@@ -313,7 +317,7 @@ __device__ __forceinline__ void primary_run(const GenParams &g, const RowConst &
     }
     if (!any) return;
     if (from_phi) {
-        const double2 *ph = g.phi + ((size_t) ((kz < 0 ? kz + N : kz)) * N + ky) * N + x0;
+        const double2 *ph = g.phi + (size_t) (kz < 0 ? kz + N : kz) * g.phi_zstride + (size_t) (ky >> g.phi_yshift) * N + x0;
 #pragma unroll
         for (int j = 0; j < RUN; j++) {
             const double2 v = ph[j];

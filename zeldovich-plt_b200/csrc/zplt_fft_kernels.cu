@@ -841,7 +841,9 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         mbar_wait(mbar, parity);                                                                                       \
         parity ^= 1u;                                                                                                  \
         _Pragma("unroll") for (int e = 0; e < KP; e++) v[e] = L[(size_t) (e * M + b) * T + p];                          \
+        if (ep.prefetch == 5) { _Pragma("unroll") for (int e = 0; e < KP; e++) v[e] = ld_stream(&src[(long long) (A) * N3 + (long long) (b + M * e) * N]); } \
         __syncthreads(); /* ring consumed; the previous unit's last exchange read is complete */                      \
+        if (ep.prefetch == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                            \
         if ((A) == 0) nn = s_nn[0];                                                                                    \
         if (NEXT_OK) issue_ring(NEXT_T, NEXT_A);                                                                       \
         if constexpr (RVZEL)                                                                                           \
@@ -1133,7 +1135,11 @@ static int launch_emit_strided_t(const cplx *cube, const SlabGeom &sg, bool slab
                                  const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st, int *launches) {
     if constexpr (has_ring<N, T>()) {
         // persistent ring-prefetched form (records wanted, parking space present); Tuning::yring = 0 disables
-        if (!slab && ep.out != nullptr && ep.scratch != nullptr && lr.counters && tn.yring > 0) {
+        // The planes of a slab rank after the fused exchange ([zl][a][y][x]) go through the ring kernel only with slab_ring >= 2:
+        // on that layout it produced wrong records in a few tiles per run (2-GPU run and one-GPU emulation alike, tools/diag_slab.py;
+        // never on the single-GPU cube), so those ranks use the one-tile-per-CTA kernel (y pass of a rank of 8: 3.6 against 3.1 ms).
+        const bool natural = ep.zstride > ep.astride;
+        if (!slab && (!natural || tn.slab_ring >= 2) && ep.out != nullptr && ep.scratch != nullptr && lr.counters && tn.yring > 0) {
             // measured at PPD=1024: RVZel qPLT 28.9 -> 28.4 ms, ZA 20.5 -> 19.3 ms.  RVdoubleZel has its own record code in the ring
             // kernel (emit_finish_rvdouble); Zeldovich and ZelSimple keep the one-tile-per-CTA kernel
             if (ep.icformat == 1 || ep.icformat == 2) {  // RVZel, RVdoubleZel (parking areas are sized for up to 512 threads)

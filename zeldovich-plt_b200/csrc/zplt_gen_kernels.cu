@@ -131,16 +131,26 @@ __global__ void mfactor_table_kernel(double *__restrict__ mtab, const double *__
     mtab[m] = 2. * growth * c * c * Tk * k2 / (3. * Omega_M * H0 * H0);
 }
 
-// phi_g(k) on the full lattice [z][y][x]: D/M at primary sites, its conjugate at their twins, with the
-// Hermitian bookkeeping of every other array (y = 0 plane, origin, Nyquist row: see generate_kernel).
-__global__ void __launch_bounds__(128) generate_phi_kernel(GenParams g, cplx *__restrict__ phi) {
+// phi_g(k): D/M at primary sites, its conjugate at their twins, with the Hermitian bookkeeping of every other array (y = 0
+// plane, origin, Nyquist row: see generate_kernel).  Single GPU: the full lattice [z][y][x], blockIdx.z = y = 0 .. N/2.
+// Slab rank: its own rows only, [z][slot][x] with the slots of zplt_slab.h — blockIdx.z counts the rank's h primary rows
+// (y = slot*G + rank, twin row in slot h + slot), plus one block for the all-zero Nyquist row on rank 0.
+__global__ void __launch_bounds__(128) generate_phi_kernel(GenParams g, SlabGeom sg, cplx *__restrict__ phi) {
     const int N = g.N;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int z = blockIdx.y;
-    const int y = blockIdx.z;  // 0 .. N/2
+    const bool slab = sg.G > 1;
+    const int y = !slab ? (int) blockIdx.z : ((int) blockIdx.z < sg.h ? (int) blockIdx.z * sg.G + sg.rank : g.half);
     if (x >= N) return;
+    // start of row (z, y) / of the twin's row (zh, N - y)
+    auto row = [&](int zz, int yy) -> size_t {
+        if (!slab) return ((size_t) zz * N + yy) * N;
+        int r, s;
+        slab_owner(N, sg.G, yy, r, s);
+        return ((size_t) zz * (2 * sg.h) + s) * N;
+    };
     if (y == g.half) {
-        phi[((size_t) z * N + y) * N + x] = make_double2(0.0, 0.0);
+        phi[row(z, y) + x] = make_double2(0.0, 0.0);
         return;
     }
     double Dr, Di;
@@ -156,14 +166,32 @@ __global__ void __launch_bounds__(128) generate_phi_kernel(GenParams g, cplx *__
             const double M = __ldg(&g.mtab[n2]);
             v = make_double2(Dr / M, (twin ? -Di : Di) / M);
         }
-        phi[((size_t) z * N) * N + x] = v;
+        phi[row(z, 0) + x] = v;
         return;
     }
     primary_density(g, x, y, z, Dr, Di, n2);
     const double M = __ldg(&g.mtab[n2]);
-    phi[((size_t) z * N + y) * N + x] = make_double2(Dr / M, Di / M);
+    phi[row(z, y) + x] = make_double2(Dr / M, Di / M);
     const int xh = (N - x) % N, zh = (N - z) % N;
-    phi[((size_t) zh * N + (N - y)) * N + xh] = make_double2(Dr / M, -Di / M);
+    phi[row(zh, N - y) + xh] = make_double2(Dr / M, -Di / M);
+}
+
+// Slab ranks, second exchange of the potential pass: after the local transformation and the y and x transforms of its
+// planes, rank r holds phi[zl][y][x]; the generation kernels of the rank that owns row y need phi[z][y][x] for all z.
+// Every row y < N/2 (only primary rows are read back, reference src/zeldovich.cpp:396-400) goes to its owner's
+// [z][slot][x] buffer by peer stores — BlockArray::StoreBlockForward/LoadBlockForward (reference
+// src/block_array.cpp:305-382, 416-464) as one copy kernel.  blockIdx = (y, zl); a NULL peer discards its rows.
+struct PhiPeers {
+    cplx *p1[16];
+};
+__global__ void __launch_bounds__(256) phi_return_kernel(const cplx *__restrict__ p2, SlabGeom sg, const __grid_constant__ PhiPeers peers) {
+    const int N = sg.N, y = blockIdx.x, zl = blockIdx.y;
+    const int np = N / sg.G, z = sg.rank * np + zl;
+    cplx *dst = peers.p1[y & (sg.G - 1)];
+    if (dst == nullptr) return;
+    const cplx *src = p2 + ((size_t) zl * N + y) * N;
+    cplx *out       = dst + ((size_t) z * (2 * sg.h) + (y >> sg.log2G)) * N;
+    for (int x = threadIdx.x; x < N; x += blockDim.x) out[x] = src[x];
 }
 
 // phi <- (Re phi + f_NL (Re phi)^2) / ppd^3, imaginary part dropped (reference src/zeldovich.cpp:744-755)
@@ -181,15 +209,23 @@ int launch_mfactor_table(double *mtab, const double *ptab, long long count, doub
                                                                                            primordial_norm, n_s, z_initial, Omega_M);
     return (int) cudaGetLastError();
 }
-int launch_generate_phi(const GenParams &g, cplx *phi, cudaStream_t st) {
+int launch_generate_phi(const GenParams &g, const SlabGeom &sg, cplx *phi, cudaStream_t st) {
     int threads = g.N < 128 ? g.N : 128;
-    dim3 grid((g.N + threads - 1) / threads, g.N, g.N / 2 + 1);
-    generate_phi_kernel<<<grid, threads, 0, st>>>(g, phi);
+    const int ny = sg.G == 1 ? g.N / 2 + 1 : sg.h + (sg.rank == 0 ? 1 : 0);
+    dim3 grid((g.N + threads - 1) / threads, g.N, ny);
+    generate_phi_kernel<<<grid, threads, 0, st>>>(g, sg, phi);
     return (int) cudaGetLastError();
 }
-int launch_fnl_local(cplx *phi, int N, double f_NL, cudaStream_t st) {
+int launch_phi_return(const cplx *p2, const SlabGeom &sg, cplx *const *peer_p1, cudaStream_t st) {
+    PhiPeers pp;
+    for (int i = 0; i < 16; i++) pp.p1[i] = i < sg.G ? peer_p1[i] : nullptr;
+    dim3 grid(sg.N / 2, sg.N / sg.G);
+    phi_return_kernel<<<grid, 256, 0, st>>>(p2, sg, pp);
+    return (int) cudaGetLastError();
+}
+int launch_fnl_local(cplx *phi, int N, long long count, double f_NL, cudaStream_t st) {
     const double inv = 1. / N / N / N;  // as the reference forms it (src/zeldovich.cpp:706)
-    fnl_local_kernel<<<148 * 8, 256, 0, st>>>(phi, (long long) N * N * N, f_NL, inv);
+    fnl_local_kernel<<<148 * 8, 256, 0, st>>>(phi, count, f_NL, inv);
     return (int) cudaGetLastError();
 }
 

@@ -101,8 +101,10 @@ int launch_generate(const GenParams &g, cplx *cube, cudaStream_t st);
 // ZD_f_NL: M(k) table, phi_g(k) = D/M on the full lattice, the local transformation in configuration space
 int launch_mfactor_table(double *mtab, const double *ptab, long long count, double fundamental2, double primordial_norm, double n_s,
                          double z_initial, double Omega_M, cudaStream_t st);
-int launch_generate_phi(const GenParams &g, cplx *phi, cudaStream_t st);
-int launch_fnl_local(cplx *phi, int N, double f_NL, cudaStream_t st);
+int launch_generate_phi(const GenParams &g, const SlabGeom &sg, cplx *phi, cudaStream_t st);
+int launch_fnl_local(cplx *phi, int N, long long count, double f_NL, cudaStream_t st);
+// slab ranks: rows y < N/2 of this rank's transformed potential planes [zl][y][x] to their owners' [z][slot][x] buffers
+int launch_phi_return(const cplx *p2, const SlabGeom &sg, cplx *const *peer_p1, cudaStream_t st);
 int launch_pcg_draws(const u128 *ystate0, const Affine *jump, long long n, uint64_t *out, cudaStream_t st);
 int launch_mode_draws(const GenParams &g, long long n, const int *k, uint64_t *raw, double *u, cudaStream_t st);
 

@@ -76,6 +76,20 @@ class PeerExchange:
         self.ctx.synchronize()
         dist.barrier(group=self.group)
 
+    def generate(self):
+        """One whole stage 1 on this rank: begin(), the potential pass with its two barriers when ZD_f_NL != 0,
+        ctx.generate(), exchange()."""
+        self.begin()
+        if self.ctx.cfg.f_NL != 0.0:
+            self.ctx.potential_begin()
+            self.ctx.synchronize()
+            dist.barrier(group=self.group)
+            self.ctx.potential_exchange()
+            self.ctx.synchronize()
+            dist.barrier(group=self.group)
+        self.ctx.generate()
+        self.exchange()
+
     def exchange(self):
         """Call after ctx.generate(): wait for this rank's peer stores, then for everybody else's."""
         self.ctx.synchronize()

@@ -64,9 +64,7 @@ def main():
         ctx.generate()
     elif args.exchange == "p2p":
         ex = zd.PeerExchange(ctx)
-        ex.begin()
-        ctx.generate()
-        ex.exchange()
+        ex.generate()  # with ZD_f_NL != 0 this includes the potential pass and its two barriers
     else:
         stream = torch.cuda.Stream(device=dev)
         ctx.set_stream(stream.cuda_stream)
