@@ -529,6 +529,7 @@ def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
             c.set_option(k, v)
         c.set_workspace(b.data_ptr(), b.numel() * 8)
         b.fill_(float("nan"))  # every row of every receive buffer must be written by somebody
+    torch.cuda.synchronize()  # the fills run on torch's stream, the library on its own (non-blocking) streams
     for c in ctxs:
         c.dbg_set_peers([b.data_ptr() + half_bytes for b in bufs])
     if kw.get("f_NL", 0.0) != 0.0:
@@ -597,6 +598,7 @@ def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit, dit_emit):
         worst = 0.0
         for target, planes in ((0, (0, 1)), (G - 1, (2, 3))):
             W[ws // 16:].fill_(float("nan"))
+            torch.cuda.synchronize()  # the fill runs on torch's stream, the library on its own (non-blocking) streams
             tctx = None
             for src in range(G):
                 c = ctx_from(pkg, P, power, src, G)

@@ -50,6 +50,7 @@ def main():
     for c, b in zip(ctxs, bufs):
         c.set_workspace(b.data_ptr(), b.numel() * 8)
         b.fill_(float("nan"))
+    torch.cuda.synchronize()  # the NaN fills run on torch's stream, the library on its own (non-blocking) streams
     for c in ctxs:
         c.dbg_set_peers([b.data_ptr() + half for b in bufs])
     for c in ctxs:
