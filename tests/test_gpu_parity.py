@@ -501,6 +501,9 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     (4, {}, dict(ppd=64, icformat="RVZel")),
     (8, {}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
     (8, {"slab_ring": 0, "yring": 0, "slab_groups": 3}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    (8, {"p2p_resident": 0}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    (4, {"p2p_resident": 0, "slab_ring": 0}, dict(ppd=128, icformat="RVdoubleZel")),
+    (4, {"slab_ring": 2}, dict(ppd=512, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
     (2, {"slab_groups": 1, "p2p_ctas": 0}, dict(ppd=128, k_cutoff=2.0, icformat="Zeldovich")),
     (4, {}, dict(ppd=512, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
     # ZD_f_NL on slab ranks: the potential pass with its own two exchanges (reference src/zeldovich.cpp:699-790, 945-960)
@@ -541,8 +544,9 @@ def test_fused_exchange_single_gpu(pkg, oracle, G, opts, case):
             c.potential_exchange()
         torch.cuda.synchronize()
     for c in ctxs:
+        # one rank at a time: the z pass of a rank is resident on half of the SMs until its generation kernels are done, and
+        # several contexts doing that on ONE GPU at once (only this emulation does) would leave no SM to the generation kernels
         c.generate()
-    for c in ctxs:
         c.synchronize()
     torch.cuda.synchronize()
     parts, var, md = [], 0.0, np.zeros(3)

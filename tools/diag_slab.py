@@ -55,6 +55,7 @@ def main():
         c.dbg_set_peers([b.data_ptr() + half for b in bufs])
     for c in ctxs:
         c.generate()
+        c.synchronize()  # one resident z pass at a time on this GPU
     torch.cuda.synchronize()
     parts = []
     for c in ctxs:

@@ -42,6 +42,7 @@ for c in ctxs:
     c.dbg_set_peers([b.data_ptr() + half for b in bufs])
 for c in ctxs:
     c.generate()
+    c.synchronize()  # one resident z pass at a time on this GPU
 torch.cuda.synchronize()
 for c in ctxs:
     c.exchange_done()

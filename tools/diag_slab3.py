@@ -59,6 +59,7 @@ for nanfill, first_ring, sync_each in ((True, True, False), (False, True, False)
         c.dbg_set_peers([b.data_ptr() + half for b in bufs])
     for c in ctxs:
         c.generate()
+        c.synchronize()  # one resident z pass at a time on this GPU
         if sync_each:
             torch.cuda.synchronize()
     torch.cuda.synchronize()

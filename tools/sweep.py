@@ -22,23 +22,22 @@ from __graft_entry__ import PKG_DIR, load_package, load_synth  # noqa: E402
 
 VARIANTS = {
     "default": {},
-    "ctas48": {"p2p_ctas": 48},
-    "ctas80": {"p2p_ctas": 80},
-    "ctas96": {"p2p_ctas": 96},
+    "ctas56": {"p2p_ctas": 56},
+    "ctas64": {"p2p_ctas": 64},
+    "ctas74": {"p2p_ctas": 74},
     "groups8": {"slab_groups": 8},
-    "groups8_ctas96 (round 1)": {"slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
-    "noring": {"slab_ring": 0},
+    "per-group launches, 64 CTAs": {"p2p_resident": 0, "p2p_ctas": 64},
+    "per-group launches, 96 CTAs, 8 groups, no ring (round 1)": {"p2p_resident": 0, "slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
 }
 VARIANTS_2048 = {
     "default": {},
-    "ctas48": {"p2p_ctas": 48},
-    "ctas96": {"p2p_ctas": 96},
-    "ctas0": {"p2p_ctas": 0},
+    "ctas64": {"p2p_ctas": 64},
+    "ctas84": {"p2p_ctas": 84},
+    "ctas98": {"p2p_ctas": 98},
     "groups8": {"slab_groups": 8},
-    "dit0 (4-pencil z pass)": {"dit2048": 0},
-    "dit_emit": {"dit2048_emit": 1},
+    "per-group launches, 96 CTAs": {"p2p_resident": 0, "p2p_ctas": 96},
 }
-DEFAULTS = {"p2p_ctas": 64, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0}
+DEFAULTS = {"p2p_ctas": 72, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1}
 
 
 def main():

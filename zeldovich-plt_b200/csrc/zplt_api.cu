@@ -116,6 +116,7 @@ struct zplt_ctx {
     cudaEvent_t ev_emit[2 * ZPLT_MAX_EMIT_EVENTS];
     int n_emit_ev;
     int launches[4];
+    unsigned int *group_flags;  // [32]: [j] set when the generation kernel of row group j has completed (resident z pass), [31] = time-out marker
     Tuning tn;     // switches: environment defaults read once in zplt_create, zplt_set_option afterwards
     LaunchRes lr;  // work counters of the persistent kernels, SM count
 };
@@ -127,7 +128,7 @@ static void tuning_from_env(Tuning &t) {
         int *v;
     } tab[] = {{"ZPLT_ZRING", &t.zring},           {"ZPLT_YRING", &t.yring},           {"ZPLT_WIDE_RECORDS", &t.wide_records},
                {"ZPLT_EMIT_SCRATCH", &t.emit_scratch}, {"ZPLT_EMIT_PREFETCH", &t.emit_prefetch}, {"ZPLT_SLAB_GROUPS", &t.slab_groups},
-               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring},
+               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring}, {"ZPLT_P2P_RESIDENT", &t.p2p_resident},
                {"ZPLT_GEN_PERSIST", &t.gen_persist}};
     for (auto &e : tab) {
         const char *s = getenv(e.name);
@@ -143,7 +144,7 @@ extern "C" int zplt_set_option(zplt_ctx *c, const char *name, int32_t value) {
         int *v;
     } tab[] = {{"zring", &t.zring},           {"yring", &t.yring},           {"wide_records", &t.wide_records},
                {"emit_scratch", &t.emit_scratch}, {"emit_prefetch", &t.emit_prefetch}, {"slab_groups", &t.slab_groups},
-               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring},
+               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring}, {"p2p_resident", &t.p2p_resident},
                {"gen_persist", &t.gen_persist}};
     for (auto &e : tab)
         if (!strcmp(e.name, name)) {
@@ -227,6 +228,8 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     c->lr     = LaunchRes();
     c->lr.sms = prop.multiProcessorCount;
     CK(cudaMalloc((void **) &c->lr.counters, 64 * sizeof(unsigned int)));
+    CK(cudaMalloc((void **) &c->group_flags, 32 * sizeof(unsigned int)));
+    CK(cudaMemset(c->group_flags, 0, 32 * sizeof(unsigned int)));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {
@@ -350,6 +353,7 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     cudaFree(c->phi);
     cudaFree(c->mtab);
     cudaFree(c->lr.counters);
+    cudaFree(c->group_flags);
     for (int i = 0; i < 2; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
         if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -561,7 +565,7 @@ extern "C" int zplt_potential_begin(zplt_ctx *c) {
     for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->slab_elems + c->phi_elems : nullptr;
     Tuning tn   = c->tn;
     tn.p2p_ctas = 0;  // nothing runs beside it
-    CK(launch_fft_tiles_p2p_any(N, T, P1, s1, peers, c->tw, tn, c->lr, c->stream));
+    CK(launch_fft_tiles_p2p_any(N, T, P1, s1, peers, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1}, c->stream));
     c->phi_stage = 1;
     return ZPLT_OK;
 }
@@ -649,20 +653,38 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         if (J < 1) J = 1;
         if (J > 16) J = 16;
         while (J > 1 && (c->sg.h % J)) J--;
-        // The two kernels share the SMs: the z pass is capped (Tuning::p2p_ctas CTAs, each fills an SM) at what keeps the
-        // links busy, generation takes the rest.  Measured on 2 GPUs at PPD=1024 (stage 1): 96 CTAs 42.5 ms, 64 CTAs 37.2 ms,
-        // uncapped 50.5 ms — with a static split stage 1 ~ max(z SM-time * 148/n, link time, gen SM-time * 148/(148-n)).
-        // The z pass of the last group has no generation left to share with and takes every SM.
+        // The two kernels share the SMs: the z pass (each of its CTAs fills an SM) gets Tuning::p2p_ctas of them, generation the
+        // rest; stage 1 ~ max(z SM-time * 148/n, link time, generation SM-time * 148/(148-n)).  p2p_resident: ONE launch of the
+        // z pass for all groups, made before the generation kernels so that its CTAs hold their SMs from the start; it consumes
+        // group j once flags[j] is set (a stream-ordered memset after the generation kernel of group j).  Launched per group
+        // instead (p2p_resident = 0), its CTAs have to win whole SMs back from two-per-SM generation CTAs and mostly run after
+        // them: measured on 8 GPUs at PPD=1024, generation done after 8.0 ms, z pass only after 14.7 ms (link time ~11 ms).
         SlabGeom sg = c->sg;
         sg.nly      = c->sg.h / J;
-        for (int j = 0; j < J; j++) {
-            sg.ly0 = j * sg.nly;
-            CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->tn, c->lr, false, c->stream));
-            CK(cudaEventRecord(c->ev_group[j], c->stream));
-            CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[j], 0));
-            Tuning tn = c->tn;
-            if (j == J - 1) tn.p2p_ctas = 0;
-            CK(launch_fft_tiles_p2p_any(c->N, fft_tile_T(c->N), c->cube, sg, c->peer_recv, c->tw, tn, c->lr, c->xchg_stream));
+        const int T = fft_tile_T(c->N);
+        if (c->tn.p2p_resident > 0) {
+            sg.ly0 = 0;
+            CK(cudaMemsetAsync(c->group_flags, 0, 16 * sizeof(unsigned int), c->stream));
+            CK(cudaEventRecord(c->ev_group[0], c->stream));
+            CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[0], 0));
+            CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, c->tn, c->lr, GroupSync{c->group_flags, c->group_flags + 31, J},
+                                        c->xchg_stream));
+            for (int j = 0; j < J; j++) {
+                sg.ly0 = j * sg.nly;
+                CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->tn, c->lr, false, c->stream));
+                CK(cudaMemsetAsync(c->group_flags + j, 1, sizeof(unsigned int), c->stream));
+            }
+        } else {
+            for (int j = 0; j < J; j++) {
+                sg.ly0 = j * sg.nly;
+                CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->tn, c->lr, false, c->stream));
+                CK(cudaEventRecord(c->ev_group[j], c->stream));
+                CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[j], 0));
+                Tuning tn = c->tn;
+                if (j == J - 1) tn.p2p_ctas = 0;  // the z pass of the last group has no generation left to share with
+                CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1},
+                                            c->xchg_stream));
+            }
         }
         c->launches[0] = J;
         c->launches[1] = J;
@@ -874,6 +896,15 @@ extern "C" int zplt_dbg_set_peers(zplt_ctx *c, int32_t nranks, void *const *recv
 extern "C" int zplt_exchange_done(zplt_ctx *c) {
     if (!c) return fail(ZPLT_EINVAL, "null context");
     if (!c->generated) return fail(ZPLT_ESTATE, "zplt_generate has not run");
+    if (c->p2p) {
+        unsigned int err = 0;
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpy(&err, c->group_flags + 31, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            cudaMemset(c->group_flags + 31, 0, sizeof(err));
+            return fail(ZPLT_ECUDA, "the z pass timed out waiting for a generation kernel (another context holding every SM of this GPU?)");
+        }
+    }
     c->exchanged = true;
     return ZPLT_OK;
 }

@@ -151,8 +151,10 @@ struct PeerTable2 {
 // the z pass of a slab rank at N = 2048 with the exchange fused in (see fft_tile_p2p_kernel): 128-byte peer stores into
 // the owners' stage-2 buffers B2[zl][a][y][x]; a NULL peer discards that rank's share
 __global__ void __launch_bounds__(512, 1)
-   fft2048_dit_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable2 peers, const cplx *__restrict__ tw) {
+   fft2048_dit_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable2 peers, const cplx *__restrict__ tw,
+                          GroupSync gs) {
     extern __shared__ __align__(16) unsigned char smem_dit[];
+    __shared__ int s_ok;
     double *S  = reinterpret_cast<double *>(smem_dit);
     cplx *park = reinterpret_cast<cplx *>(smem_dit + Split::IMAGE_BYTES);
     constexpr int N = 2048, T = Split::T, XT = N / T;
@@ -162,11 +164,24 @@ __global__ void __launch_bounds__(512, 1)
     const int np  = N / sg.G, lognp = 11 - sg.log2G;
     const int nsl = 2 * sg.nly;
     const int na  = sg.na;
-    const long long ntiles = (long long) XT * nsl * sg.na;
+    const long long tpg = (long long) XT * nsl * sg.na, ntiles = tpg * gs.J;  // tiles are numbered group by group (see p2p_tile)
+    int ready = gs.flags == nullptr ? gs.J : -1;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int xt = (int) (t % XT);
-        const int rr = (int) (t / XT), sidx = rr % nsl, a = rr / nsl;
-        const int slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
+        const int grp      = (int) (t / tpg);
+        const long long tt = t - grp * tpg;
+        if (grp > ready) {  // CTA-uniform: wait until the generation kernel of this row group has completed
+            if (tid == 0) s_ok = wait_group(gs.flags, grp) ? 1 : 0;
+            __syncthreads();
+            if (!s_ok) {
+                if (tid == 0) atomicExch(gs.err, 1u);
+                return;
+            }
+            ready = grp;
+        }
+        const int xt = (int) (tt % XT);
+        const int rr = (int) (tt / XT), sidx = rr % nsl, a = rr / nsl;
+        const int ly0  = sg.ly0 + grp * sg.nly;
+        const int slot = sidx < sg.nly ? ly0 + sidx : sg.h + ly0 + (sidx - sg.nly);
         const int row  = a * 2 * sg.h + slot;
         const int x    = xt * T + p;
         const int y    = slab_row(N, sg.G, sg.rank, slot);
@@ -319,21 +334,22 @@ int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &g, const cplx
 }
 
 int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
-                             const Tuning &tn, LaunchRes &lr, cudaStream_t st) {
+                             const Tuning &tn, LaunchRes &lr, const GroupSync &gs, cudaStream_t st) {
     if (N == 2048 && tn.dit2048 > 0 && sg.G <= 16) {
         cudaError_t e = cudaFuncSetAttribute(fft2048_dit_p2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DIT_SMEM);
         if (e != cudaSuccess) return (int) e;
         PeerTable2 pt;
         for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
-        const long long ntiles = (long long) (N / 8) * 2 * sg.nly * sg.na;
+        const long long ntiles = (long long) (N / 8) * 2 * sg.nly * sg.na * gs.J;
         long long nctas = lr.sms;
-        const int lim   = tn.p2p_ctas;  // as fft_tile_p2p_kernel: leave SMs to the overlapped generation kernel
+        int lim         = tn.p2p_ctas;  // as fft_tile_p2p_kernel: leave SMs to the overlapped generation kernels
+        if (gs.flags != nullptr && (lim <= 0 || lim > (lr.sms * 2) / 3)) lim = (lr.sms * 2) / 3;
         if (lim > 0 && lim < nctas) nctas = lim;
         if (nctas > ntiles) nctas = ntiles;
-        fft2048_dit_p2p_kernel<<<(unsigned) nctas, 512, DIT_SMEM, st>>>(b1, sg, pt, tw);
+        fft2048_dit_p2p_kernel<<<(unsigned) nctas, 512, DIT_SMEM, st>>>(b1, sg, pt, tw, gs);
         return (int) cudaGetLastError();
     }
-    return launch_fft_tiles_p2p(N, T, b1, sg, peer_recv, tw, tn, lr, st);
+    return launch_fft_tiles_p2p(N, T, b1, sg, peer_recv, tw, tn, lr, gs, st);
 }
 
 // y pass + emission of planes [z_first, z_first + nz) with the 8-pencil decimation kernel; returns -1 when this launch

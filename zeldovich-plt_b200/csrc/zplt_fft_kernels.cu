@@ -269,32 +269,48 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
 struct PeerTable {
     cplx *recv[16];
 };
-// tile t of a (group of a) stage-1 buffer -> x tile, packed array, slot
-__device__ __forceinline__ void p2p_tile(const SlabGeom &sg, int XT, long long t, int &xt, int &a, int &slot) {
-    const int nsl = 2 * sg.nly;
-    xt            = (int) (t % XT);
-    const int rr = (int) (t / XT), sidx = rr % nsl;
-    a    = rr / nsl;
-    slot = sidx < sg.nly ? sg.ly0 + sidx : sg.h + sg.ly0 + (sidx - sg.nly);
+// tile t of the stage-1 buffer -> x tile, packed array, slot, row group.  Tiles are numbered group by group (sg.nly primary
+// rows per group, starting at row sg.ly0), so that a launch covering several groups meets them in the order they are generated.
+__device__ __forceinline__ void p2p_tile(const SlabGeom &sg, int XT, long long t, int &xt, int &a, int &slot, int &grp) {
+    const int nsl       = 2 * sg.nly;
+    const long long tpg = (long long) XT * nsl * sg.na;
+    grp                 = (int) (t / tpg);
+    const long long tt  = t - grp * tpg;
+    xt                  = (int) (tt % XT);
+    const int rr = (int) (tt / XT), sidx = rr % nsl;
+    a             = rr / nsl;
+    const int ly0 = sg.ly0 + grp * sg.nly;
+    slot          = sidx < sg.nly ? ly0 + sidx : sg.h + ly0 + (sidx - sg.nly);
 }
 template <int N, int T>
 __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
-   fft_tile_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable peers, const cplx *__restrict__ tw) {
+   fft_tile_p2p_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable peers, const cplx *__restrict__ tw,
+                       GroupSync gs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ok;
     cplx *S         = reinterpret_cast<cplx *>(smem_raw);
     constexpr int M = N / 16;
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     const int rows = sg.na * 2 * sg.h;  // x-rows per z plane of the stage-1 buffer
     const long long nstride = (long long) rows * N;
     const int np = N / sg.G, lognp = FftLog2<N>::value - sg.log2G;
-    // persistent CTAs over the tiles (x tile, array, slot of this group): the pass is NVLink-bound, so
-    // a limited number of CTAs saturates the links and leaves the other SMs to the generation
-    // kernel of the next group, which runs concurrently on another stream
+    // persistent CTAs over the tiles (x tile, array, slot): the pass is NVLink-bound, so a limited number of CTAs
+    // saturates the links and leaves the other SMs to the generation kernels, which run concurrently on another stream
     constexpr int XT = N / T;
-    const long long ntiles = (long long) XT * 2 * sg.nly * sg.na;
+    const long long ntiles = (long long) XT * 2 * sg.nly * sg.na * gs.J;
+    int ready = gs.flags == nullptr ? gs.J : -1;  // groups known to be generated
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int xt, a, slot;
-        p2p_tile(sg, XT, t, xt, a, slot);
+        int xt, a, slot, grp;
+        p2p_tile(sg, XT, t, xt, a, slot, grp);
+        if (grp > ready) {  // CTA-uniform
+            if (tid == 0) s_ok = wait_group(gs.flags, grp) ? 1 : 0;
+            __syncthreads();
+            if (!s_ok) {
+                if (tid == 0) atomicExch(gs.err, 1u);
+                return;
+            }
+            ready = grp;
+        }
         const int row  = a * 2 * sg.h + slot;
         const int x    = xt * T + p;
         const int y    = slab_row(N, sg.G, sg.rank, slot);
@@ -316,27 +332,40 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
 
 // The same pass with the TMA ring of fft_tile_ring_kernel on the load side: while one tile is transformed and sent,
 // KP of the 16 slices of the CTA's next tile land in shared memory, so the links never wait for the local HBM reads
-// (the plain kernel alternates: load, transform, store).  Tiles come from a device counter.
+// (the plain kernel alternates: load, transform, store).  Tiles come from a device counter.  With GroupSync::flags the
+// launch covers every row group of stage 1: the CTAs hold their SMs from the start (a static split of the SMs between this
+// pass and the generation kernels — CTAs launched per group had to win whole SMs back from two-per-SM generation CTAs and
+// mostly ran after them) and wait, one tile ahead, for the group of the next tile to be generated.
 template <int N, int T, int KP>
 __global__ void __launch_bounds__(T *(N / 16), 1)
    fft_tile_p2p_ring_kernel(const cplx *__restrict__ b1, SlabGeom sg, const __grid_constant__ PeerTable peers, const cplx *__restrict__ tw,
-                            unsigned int *__restrict__ counter, const __grid_constant__ CUtensorMap tmap) {
+                            unsigned int *__restrict__ counter, const __grid_constant__ CUtensorMap tmap, GroupSync gs) {
     extern __shared__ __align__(128) unsigned char smem_ring[];
     constexpr int M  = N / 16;
     constexpr int XT = N / T;
     cplx *S            = reinterpret_cast<cplx *>(smem_ring);
     cplx *L            = reinterpret_cast<cplx *>(smem_ring + RingSmem<N, T>::EXCHANGE);  // [KP][M][T]
     uint64_t *mbar     = reinterpret_cast<uint64_t *>(smem_ring + RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx));
-    unsigned int *s_nn = reinterpret_cast<unsigned int *>(mbar + 1);
+    unsigned int *s_nn = reinterpret_cast<unsigned int *>(mbar + 1);  // [0], [1]: tiles handed out; [2]: a wait timed out
     const int tid = threadIdx.x, p = tid % T, b = tid / T;
     const int rows = sg.na * 2 * sg.h;
     const long long nstride = (long long) rows * N;
     const int np = N / sg.G, lognp = FftLog2<N>::value - sg.log2G;
-    const unsigned int ntiles = (unsigned int) (XT * 2 * sg.nly * sg.na);
+    const unsigned int tpg = (unsigned int) (XT * 2 * sg.nly * sg.na), ntiles = tpg * (unsigned int) gs.J;
+    int ready = gs.flags == nullptr ? gs.J : -1;  // thread 0: groups known to be generated
+    auto ensure = [&](unsigned int t) {           // thread 0: the rows of tile t exist
+        if (t < ntiles) {
+            const int grp = (int) (t / tpg);
+            if (grp > ready) {
+                if (!wait_group(gs.flags, grp)) s_nn[2] = 1u;
+                ready = grp;
+            }
+        }
+    };
     auto issue_ring = [&](unsigned int t) {
         if (tid == 0) {
-            int xt, a, slot;
-            p2p_tile(sg, XT, t, xt, a, slot);
+            int xt, a, slot, grp;
+            p2p_tile(sg, XT, t, xt, a, slot, grp);
             mbar_expect_tx(mbar, (unsigned) (KP * M * T * sizeof(cplx)));
 #pragma unroll
             for (int e = 0; e < KP; e++) tma_load_4d(L + (size_t) e * M * T, &tmap, xt * 2 * T, a * 2 * sg.h + slot, M * e, 0, mbar);
@@ -346,16 +375,25 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         mbar_init(mbar, 1);
         s_nn[0] = atomicAdd(counter, 1u);
         s_nn[1] = atomicAdd(counter, 1u);
+        s_nn[2] = 0u;
+        ensure(s_nn[0]);
     }
     __syncthreads();
     unsigned int cur = s_nn[0], nxt = s_nn[1];
+    if (s_nn[2]) {
+        if (tid == 0) atomicExch(gs.err, 1u);
+        return;
+    }
     __syncthreads();
     if (cur < ntiles) issue_ring(cur);
     unsigned int parity = 0;
     while (cur < ntiles) {
-        if (tid == 0) s_nn[0] = atomicAdd(counter, 1u);  // the tile after next
-        int xt, a, slot;
-        p2p_tile(sg, XT, cur, xt, a, slot);
+        if (tid == 0) {
+            s_nn[0] = atomicAdd(counter, 1u);  // the tile after next
+            ensure(nxt);                       // before anybody passes this iteration's barrier: its ring and plain loads come after it
+        }
+        int xt, a, slot, grp;
+        p2p_tile(sg, XT, cur, xt, a, slot, grp);
         const int row = a * 2 * sg.h + slot;
         const int x   = xt * T + p;
         const int y   = slab_row(N, sg.G, sg.rank, slot);
@@ -370,6 +408,10 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         for (int e = 0; e < KP; e++) v[e] = L[(size_t) (e * M + b) * T + p];
         __syncthreads();  // the ring has been read and the exchange image of the previous tile is no longer in use
         const unsigned int nn = s_nn[0];
+        if (s_nn[2]) {  // CTA-uniform: nothing is in flight here (the ring of `cur` is consumed, that of `nxt` not yet requested)
+            if (tid == 0) atomicExch(gs.err, 1u);
+            return;
+        }
         if (nxt < ntiles) issue_ring(nxt);
         const int bo = fft_pencil<N, T>(v, S + p * FftSmem<N, T>::PSTRIDE, b, tw);
 #pragma unroll
@@ -1036,18 +1078,21 @@ int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *
     return (int) cudaErrorInvalidValue;
 }
 
+// gs.flags != NULL: one launch for all gs.J row groups of stage 1 (sg.nly rows each), gated by the flags; its CTAs stay resident
+// while the generation kernels run, so they must leave SMs to them: at most half of the device
 template <int N, int T>
 static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,
-                              LaunchRes &lr, cudaStream_t st) {
+                              LaunchRes &lr, const GroupSync &gs, cudaStream_t st) {
     PeerTable pt;
     for (int i = 0; i < 16; i++) pt.recv[i] = i < sg.G ? peer_recv[i] : nullptr;
-    const long long ntiles = (long long) (N / T) * 2 * sg.nly * sg.na;
-    // about two thirds of the SMs keep NVLink saturated and leave room for the overlapped generation kernel
-    const int lim = tn.p2p_ctas;  // 0: as many as fit
+    const long long ntiles = (long long) (N / T) * 2 * sg.nly * sg.na * gs.J;
+    // the CTAs of this pass and those of the generation kernels share the SMs (see run_generate)
+    int lim = tn.p2p_ctas;  // 0: as many as fit
+    if (gs.flags != nullptr && (lim <= 0 || lim > lr.sms / 2)) lim = lr.sms / 2;
     if constexpr (has_ring<N, T>()) {
         if (tn.slab_ring > 0 && lr.counters && ntiles < (1ll << 31)) {
             constexpr int M = N / 16, KP = 12;
-            const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 16;
+            const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 32;
             cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_ring_kernel<N, T, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
             if (e != cudaSuccess) return (int) e;
             unsigned int *ctr = tile_counter(lr, st);
@@ -1063,30 +1108,32 @@ static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *p
                                            (cuuint64_t) rows * N * N * sizeof(cplx)};
             const cuuint32_t box[4]     = {2 * T, 1, (cuuint32_t) M, 1};
             if (int rc = encode_tmap4(&tmap, b1, dims, strides, box)) return rc;
-            fft_tile_p2p_ring_kernel<N, T, KP><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw, ctr, tmap);
+            fft_tile_p2p_ring_kernel<N, T, KP><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw, ctr, tmap, gs);
             return (int) cudaGetLastError();
         }
     }
     size_t smem = fft_tile_smem(N, T);
     cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
-    long long nctas = persistent_ctas((const void *) fft_tile_p2p_kernel<N, T>, T * (N / 16), smem, lr.sms);
-    if (lim > 0 && lim < nctas) nctas = lim;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_tile_p2p_kernel<N, T>, T * (N / 16), smem);
+    if (per_sm < 1) per_sm = 1;
+    long long nctas = (long long) (lim > 0 && lim < lr.sms ? lim : lr.sms) * per_sm;  // lim counts SMs
     if (nctas > ntiles) nctas = ntiles;
-    fft_tile_p2p_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw);
+    fft_tile_p2p_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw, gs);
     return (int) cudaGetLastError();
 }
 
 int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,
-                         LaunchRes &lr, cudaStream_t st) {
+                         LaunchRes &lr, const GroupSync &gs, cudaStream_t st) {
     if (sg.G > 16) return (int) cudaErrorInvalidValue;
-    ZPLT_CASE(launch_tiles_p2p_t, 32, 32, b1, sg, peer_recv, tw, tn, lr, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 64, 32, b1, sg, peer_recv, tw, tn, lr, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 128, 16, b1, sg, peer_recv, tw, tn, lr, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 256, 16, b1, sg, peer_recv, tw, tn, lr, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 512, 8, b1, sg, peer_recv, tw, tn, lr, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 1024, 8, b1, sg, peer_recv, tw, tn, lr, st)
-    ZPLT_CASE(launch_tiles_p2p_t, 2048, 4, b1, sg, peer_recv, tw, tn, lr, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 32, 32, b1, sg, peer_recv, tw, tn, lr, gs, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 64, 32, b1, sg, peer_recv, tw, tn, lr, gs, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 128, 16, b1, sg, peer_recv, tw, tn, lr, gs, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 256, 16, b1, sg, peer_recv, tw, tn, lr, gs, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 512, 8, b1, sg, peer_recv, tw, tn, lr, gs, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 1024, 8, b1, sg, peer_recv, tw, tn, lr, gs, st)
+    ZPLT_CASE(launch_tiles_p2p_t, 2048, 4, b1, sg, peer_recv, tw, tn, lr, gs, st)
     return (int) cudaErrorInvalidValue;
 }
 

@@ -54,11 +54,20 @@ struct Tuning {
     int emit_scratch = 1;   // ZPLT_EMIT_SCRATCH: park record halves in the L2-resident scratch (whole-record stores)
     int emit_prefetch = 1;  // ZPLT_EMIT_PREFETCH: L2-prefetch the next packed array of a tile (one-tile-per-CTA kernel)
     int slab_groups  = 16;  // ZPLT_SLAB_GROUPS: row groups of stage 1 on a slab rank (generation of group j+1 overlaps the z pass of j)
-    int p2p_ctas     = 64;  // ZPLT_P2P_CTAS: CTAs of the z pass + exchange kernel (0 = as many as fit); the last row group is not capped
+    int p2p_ctas     = 72;  // ZPLT_P2P_CTAS: SMs of the z pass + exchange kernel (0 = as many as allowed); generation takes the rest
     int dit2048      = 1;   // ZPLT_DIT2048: 8-pencil decimation kernels for the N = 2048 z pass (122 -> 77 ms per rank of 8, local stores)
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
+    int p2p_resident = 1;   // ZPLT_P2P_RESIDENT: one z pass + exchange launch for the whole of stage 1, gated by per-group flags
     int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
+};
+
+// The z pass + exchange kernel of a slab rank can be resident for the whole of stage 1 and consume row groups as the generation
+// kernels (another stream) complete them: after each generation kernel the host enqueues a stream-ordered memset of one flag.
+struct GroupSync {
+    const unsigned int *flags;  // [J] nonzero once the rows of group j have been generated; NULL: everything is ready
+    unsigned int *err;          // set to 1 when a wait times out (the kernel then gives up instead of hanging the GPU)
+    int J;                      // row groups covered by this launch
 };
 
 // Per-context launch resources: the work counters of the persistent kernels (a small rotating device array, so that
@@ -81,12 +90,12 @@ int launch_fft_tiles(int N, int T, cplx *data, const TileGeom &geom, const cplx 
 // z-axis FFT of a slab rank's stage-1 buffer with the exchange fused in: results are stored
 // directly into every owner rank's stage-2 buffer (peer_recv[r], NVLink peer memory; NULL = discard).
 int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,
-                         LaunchRes &lr, cudaStream_t st);
+                         LaunchRes &lr, const GroupSync &gs, cudaStream_t st);
 // The same two launchers behind Tuning::dit2048: at N = 2048 they use the 8-pencil decimation kernels of
 // zplt_fft2048_kernels.cu; otherwise they forward to the launchers above.
 int launch_fft_tiles_any(int N, int T, cplx *data, const TileGeom &geom, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st);
 int launch_fft_tiles_p2p_any(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw,
-                             const Tuning &tn, LaunchRes &lr, cudaStream_t st);
+                             const Tuning &tn, LaunchRes &lr, const GroupSync &gs, cudaStream_t st);
 // N = 2048 y pass + emission with 8-pencil tiles (zplt_fft2048_kernels.cu); -1 = not applicable to this launch
 int launch_fft2048_emit(const cplx *planes, long long z_first, long long nz, const EmitParams &ep, const cplx *tw, const Tuning &tn,
                         LaunchRes &lr, cudaStream_t st);

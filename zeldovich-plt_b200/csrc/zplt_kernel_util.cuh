@@ -4,6 +4,7 @@
 #include <cuda.h>  // CUtensorMap (types only)
 
 #include "zplt_device.cuh"
+#include "zplt_internal.h"
 
 namespace zplt {
 
@@ -106,6 +107,26 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, i
        : "memory");
 }
 
+
+// ------------------------------------------------------------------ waiting for another kernel's progress
+// The z pass + exchange kernel of a slab rank is resident for the whole of stage 1 and consumes row groups as the generation
+// kernels (another stream) complete them: after each generation kernel the host enqueues a stream-ordered memset of one flag.
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: true when flags[grp] is set, false after ~15 s of polling
+__device__ __forceinline__ bool wait_group(const unsigned int *flags, int grp) {
+    if (ld_volatile_u32(flags + grp) != 0u) return true;
+    const long long t0 = clock64();
+    while (ld_volatile_u32(flags + grp) == 0u) {
+        __nanosleep(256);
+        if (clock64() - t0 > 30000000000ll) return false;
+    }
+    __threadfence();
+    return true;
+}
 
 // ------------------------------------------------------------------ statistics
 __device__ __forceinline__ double warp_sum(double v) {
