@@ -192,7 +192,7 @@ int zplt_synchronize(zplt_ctx *ctx);
  * Also out[4..7] = number of kernel launches in each of those stages. */
 int zplt_get_timings(zplt_ctx *ctx, double out[8]);
 /* Tuning / diagnostic switches of a context: "zring", "yring", "wide_records", "emit_scratch", "emit_prefetch",
- * "slab_groups", "p2p_ctas", "p2p_resident", "dit2048", "dit2048_emit", "slab_ring", "gen_persist" (csrc/zplt_internal.h, struct Tuning).  Their defaults
+ * "slab_groups", "p2p_ctas", "p2p_resident", "p2p_helper", "dit2048", "dit2048_emit", "slab_ring", "gen_persist" (csrc/zplt_internal.h, struct Tuning).  Their defaults
  * come from the environment variables ZPLT_<NAME>, read once in zplt_create — nothing on the launch path calls getenv. */
 int zplt_set_option(zplt_ctx *ctx, const char *name, int32_t value);
 

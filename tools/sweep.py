@@ -26,6 +26,8 @@ VARIANTS = {
     "ctas64": {"p2p_ctas": 64},
     "ctas74": {"p2p_ctas": 74},
     "groups8": {"slab_groups": 8},
+    "no helper": {"p2p_helper": 0},
+    "ctas56 no helper": {"p2p_ctas": 56, "p2p_helper": 0},
     "per-group launches, 64 CTAs": {"p2p_resident": 0, "p2p_ctas": 64},
     "per-group launches, 96 CTAs, 8 groups, no ring (round 1)": {"p2p_resident": 0, "slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
 }
@@ -37,7 +39,7 @@ VARIANTS_2048 = {
     "groups8": {"slab_groups": 8},
     "per-group launches, 96 CTAs": {"p2p_resident": 0, "p2p_ctas": 96},
 }
-DEFAULTS = {"p2p_ctas": 72, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1}
+DEFAULTS = {"p2p_ctas": 72, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1}
 
 
 def main():

@@ -128,7 +128,7 @@ static void tuning_from_env(Tuning &t) {
         int *v;
     } tab[] = {{"ZPLT_ZRING", &t.zring},           {"ZPLT_YRING", &t.yring},           {"ZPLT_WIDE_RECORDS", &t.wide_records},
                {"ZPLT_EMIT_SCRATCH", &t.emit_scratch}, {"ZPLT_EMIT_PREFETCH", &t.emit_prefetch}, {"ZPLT_SLAB_GROUPS", &t.slab_groups},
-               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring}, {"ZPLT_P2P_RESIDENT", &t.p2p_resident},
+               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring}, {"ZPLT_P2P_RESIDENT", &t.p2p_resident}, {"ZPLT_P2P_HELPER", &t.p2p_helper},
                {"ZPLT_GEN_PERSIST", &t.gen_persist}};
     for (auto &e : tab) {
         const char *s = getenv(e.name);
@@ -144,7 +144,7 @@ extern "C" int zplt_set_option(zplt_ctx *c, const char *name, int32_t value) {
         int *v;
     } tab[] = {{"zring", &t.zring},           {"yring", &t.yring},           {"wide_records", &t.wide_records},
                {"emit_scratch", &t.emit_scratch}, {"emit_prefetch", &t.emit_prefetch}, {"slab_groups", &t.slab_groups},
-               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring}, {"p2p_resident", &t.p2p_resident},
+               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring}, {"p2p_resident", &t.p2p_resident}, {"p2p_helper", &t.p2p_helper},
                {"gen_persist", &t.gen_persist}};
     for (auto &e : tab)
         if (!strcmp(e.name, name)) {
@@ -565,7 +565,7 @@ extern "C" int zplt_potential_begin(zplt_ctx *c) {
     for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->slab_elems + c->phi_elems : nullptr;
     Tuning tn   = c->tn;
     tn.p2p_ctas = 0;  // nothing runs beside it
-    CK(launch_fft_tiles_p2p_any(N, T, P1, s1, peers, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1}, c->stream));
+    CK(launch_fft_tiles_p2p_any(N, T, P1, s1, peers, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1, nullptr}, c->stream));
     c->phi_stage = 1;
     return ZPLT_OK;
 }
@@ -664,15 +664,33 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         const int T = fft_tile_T(c->N);
         if (c->tn.p2p_resident > 0) {
             sg.ly0 = 0;
+            // everything that will run beside the waiting z pass must already be loaded (lazy module loading synchronises):
+            // the generation kernel (cube = NULL: prepare only) and the driver's memset
+            CK(launch_gen_xfft(c->N, gt, c->gp, sg, nullptr, c->tw, c->tn, c->lr, false, c->stream));
             CK(cudaMemsetAsync(c->group_flags, 0, 16 * sizeof(unsigned int), c->stream));
+            // when the pass hands out its tiles through a counter, a second launch of it joins on the SMs the generation kernels
+            // leave behind when they are done (stage 1 is SM-bound on few ranks: half of the device would idle otherwise)
+            const bool helper = c->tn.p2p_helper > 0 && !(c->N == 2048 && c->tn.dit2048 > 0) && fft_tiles_p2p_shares_tiles(c->N, c->tn);
+            unsigned int *ctr = nullptr;
+            if (helper) {
+                ctr = c->lr.counters + (c->lr.next_counter++ & 63);
+                CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), c->stream));
+            }
             CK(cudaEventRecord(c->ev_group[0], c->stream));
             CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[0], 0));
-            CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, c->tn, c->lr, GroupSync{c->group_flags, c->group_flags + 31, J},
-                                        c->xchg_stream));
+            CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, c->tn, c->lr,
+                                        GroupSync{c->group_flags, c->group_flags + 31, J, ctr}, c->xchg_stream));
             for (int j = 0; j < J; j++) {
                 sg.ly0 = j * sg.nly;
                 CK(launch_gen_xfft(c->N, gt, c->gp, sg, c->cube, c->tw, c->tn, c->lr, false, c->stream));
                 CK(cudaMemsetAsync(c->group_flags + j, 1, sizeof(unsigned int), c->stream));
+            }
+            if (helper) {
+                sg.ly0      = 0;
+                Tuning tn   = c->tn;
+                tn.p2p_ctas = 0;
+                CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, J, ctr},
+                                            c->stream));
             }
         } else {
             for (int j = 0; j < J; j++) {
@@ -682,7 +700,7 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
                 CK(cudaStreamWaitEvent(c->xchg_stream, c->ev_group[j], 0));
                 Tuning tn = c->tn;
                 if (j == J - 1) tn.p2p_ctas = 0;  // the z pass of the last group has no generation left to share with
-                CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1},
+                CK(launch_fft_tiles_p2p_any(c->N, T, c->cube, sg, c->peer_recv, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1, nullptr},
                                             c->xchg_stream));
             }
         }

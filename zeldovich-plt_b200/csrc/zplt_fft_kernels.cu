@@ -1048,6 +1048,12 @@ static int launch_genx_t(const GenParams &g, const SlabGeom &sg, cplx *cube, con
     size_t smem = fft_tile_smem(N, NP) + (size_t) 6 * N * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gen_xfft_kernel<N, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
+    if (cube == nullptr) {
+        // prepare only: make sure the kernel's code is on the device.  With lazy module loading the first launch of a kernel loads
+        // it, which synchronises with running work — fatal when the running work is the resident z pass waiting for this kernel.
+        cudaFuncAttributes fa;
+        return (int) cudaFuncGetAttributes(&fa, gen_xfft_kernel<N, NP>);
+    }
     dim3 grid(N, sg.G == 1 ? N / 2 + 1 : sg.nly + ((sg.rank == 0 && sg.ly0 == 0) ? 1 : 0), 1);
     gen_xfft_kernel<N, NP><<<grid, NP *(N / 16), smem, st>>>(g, sg, cube, tw, skip_fft ? 1 : 0);
     return (int) cudaGetLastError();
@@ -1095,7 +1101,7 @@ static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *p
             const size_t smem = RingSmem<N, T>::EXCHANGE + (size_t) KP * M * T * sizeof(cplx) + 32;
             cudaError_t e = cudaFuncSetAttribute(fft_tile_p2p_ring_kernel<N, T, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
             if (e != cudaSuccess) return (int) e;
-            unsigned int *ctr = tile_counter(lr, st);
+            unsigned int *ctr = gs.counter ? gs.counter : tile_counter(lr, st);
             if (!ctr) return (int) cudaErrorMemoryAllocation;
             long long nctas = lr.sms;
             if (lim > 0 && lim < nctas) nctas = lim;
@@ -1122,6 +1128,10 @@ static int launch_tiles_p2p_t(const cplx *b1, const SlabGeom &sg, cplx *const *p
     if (nctas > ntiles) nctas = ntiles;
     fft_tile_p2p_kernel<N, T><<<(unsigned) nctas, T *(N / 16), smem, st>>>(b1, sg, pt, tw, gs);
     return (int) cudaGetLastError();
+}
+
+bool fft_tiles_p2p_shares_tiles(int N, const Tuning &tn) {
+    return tn.slab_ring > 0 && (N == 1024 || N == 512 || N == 256 || N == 64);  // has_ring sizes: fft_tile_p2p_ring_kernel
 }
 
 int launch_fft_tiles_p2p(int N, int T, const cplx *b1, const SlabGeom &sg, cplx *const *peer_recv, const cplx *tw, const Tuning &tn,

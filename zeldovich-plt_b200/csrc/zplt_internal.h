@@ -59,6 +59,7 @@ struct Tuning {
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
     int p2p_resident = 1;   // ZPLT_P2P_RESIDENT: one z pass + exchange launch for the whole of stage 1, gated by per-group flags
+    int p2p_helper   = 1;   // ZPLT_P2P_HELPER: a second launch of it on the SMs the generation kernels leave behind when they are done
     int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
 };
 
@@ -68,7 +69,11 @@ struct GroupSync {
     const unsigned int *flags;  // [J] nonzero once the rows of group j have been generated; NULL: everything is ready
     unsigned int *err;          // set to 1 when a wait times out (the kernel then gives up instead of hanging the GPU)
     int J;                      // row groups covered by this launch
+    unsigned int *counter;      // tile counter shared with another launch of the same pass (already reset by the caller), or NULL
 };
+// true when the z pass + exchange kernel for length N hands out its tiles through a device counter (ring-prefetched form), so that
+// two launches can work through the same tiles together
+bool fft_tiles_p2p_shares_tiles(int N, const Tuning &tn);
 
 // Per-context launch resources: the work counters of the persistent kernels (a small rotating device array, so that
 // launches in flight on different streams never share one) and the device's SM count.
@@ -82,7 +87,7 @@ int fft_tile_T(int N);            // pencils per CTA used for length N (strided 
 int gen_xfft_T(int N, int na);    // pencils per CTA of the generation + x-FFT kernel
 size_t fft_tile_smem(int N, int T);
 // Fused mode generation + x-axis FFT, writes the whole [na][z][y][x] cube (skip_fft: the packed arrays as the
-// kernel forms them, without the transform — introspection of the hot kernel).
+// kernel forms them, without the transform — introspection of the hot kernel).  cube = NULL: load the kernel, launch nothing.
 int launch_gen_xfft(int N, int T, const GenParams &g, const SlabGeom &sg, cplx *cube, const cplx *tw, const Tuning &tn, LaunchRes &lr,
                     bool skip_fft, cudaStream_t st);
 // In-place backward FFT of every pencil described by geom (tiles of T pencils).  Returns cudaError_t.
