@@ -22,24 +22,21 @@ from __graft_entry__ import PKG_DIR, load_package, load_synth  # noqa: E402
 
 VARIANTS = {
     "default": {},
+    "ctas40": {"p2p_ctas": 40},
     "ctas56": {"p2p_ctas": 56},
     "ctas64": {"p2p_ctas": 64},
-    "ctas74": {"p2p_ctas": 74},
-    "groups8": {"slab_groups": 8},
     "no helper": {"p2p_helper": 0},
-    "ctas56 no helper": {"p2p_ctas": 56, "p2p_helper": 0},
     "per-group launches, 64 CTAs": {"p2p_resident": 0, "p2p_ctas": 64},
     "per-group launches, 96 CTAs, 8 groups, no ring (round 1)": {"p2p_resident": 0, "slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
 }
 VARIANTS_2048 = {
     "default": {},
-    "ctas64": {"p2p_ctas": 64},
+    "ctas56": {"p2p_ctas": 56},
     "ctas84": {"p2p_ctas": 84},
     "ctas98": {"p2p_ctas": 98},
-    "groups8": {"slab_groups": 8},
     "per-group launches, 96 CTAs": {"p2p_resident": 0, "p2p_ctas": 96},
 }
-DEFAULTS = {"p2p_ctas": 72, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1}
+DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1}
 
 
 def main():

@@ -662,6 +662,7 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         SlabGeom sg = c->sg;
         sg.nly      = c->sg.h / J;
         const int T = fft_tile_T(c->N);
+        if (c->tn.p2p_ctas < 0) c->tn.p2p_ctas = c->N >= 2048 ? 84 : 64;
         if (c->tn.p2p_resident > 0) {
             sg.ly0 = 0;
             // everything that will run beside the waiting z pass must already be loaded (lazy module loading synchronises):
