@@ -44,7 +44,8 @@ extern "C" {
 /* What the kernels need from reference class Parameters (include/parameters.h:14-74)
  * after Parameters::setup() (src/parameters.cpp:97-197). */
 typedef struct zplt_config {
-    int64_t ppd;          /* particles per dimension; power of two, 16..2048 (2048 needs nranks >= 4: HBM) */
+    int64_t ppd;          /* particles per dimension: a power of two in 16..2048 (2048 needs nranks >= 4: HBM) runs the fused kernels;
+                           * any other even ppd in 16..1024 runs the general path (Bluestein transforms, one GPU, no f_NL) */
     double boxsize;       /* BoxSize */
     int64_t seed;         /* ZD_Seed as the reference widens it: (int) sign-extended (src/power_spectrum.cpp:14) */
     double k_cutoff;      /* ZD_k_cutoff >= 1 */

@@ -557,8 +557,27 @@ static void zo_site(const zo_state *st, u128 seed_state, int64_t x, int64_t y, i
 }
 
 /* ------------------------------------------------------------ FFT ---------- */
-/* Unnormalised backward DFT (sign +1, src/zeldovich.cpp:61-62), iterative radix-2. */
+/* Unnormalised backward DFT (sign +1, src/zeldovich.cpp:61-62): iterative radix-2 for powers of two, the direct
+ * O(n^2) sum (twiddle index reduced mod n, so every phase is a table entry) for any other length — the reference takes
+ * any even ppd (src/block_array.cpp:38-40); only small non-power-of-two sizes are run through the oracle. */
 static void zo_fft1(double *re_im, int64_t n, int64_t stride, const double *tw, double *tmp) {
+    if (n & (n - 1)) {
+        for (int64_t k = 0; k < n; k++) {
+            double sr = 0.0, si = 0.0;
+            for (int64_t j = 0; j < n; j++) {
+                const int64_t t = (j * k) % n;
+                const double wr = tw[2 * t], wi = tw[2 * t + 1], ar = re_im[2 * j * stride], ai = re_im[2 * j * stride + 1];
+                sr += ar * wr - ai * wi;
+                si += ar * wi + ai * wr;
+            }
+            tmp[2 * k] = sr, tmp[2 * k + 1] = si;
+        }
+        for (int64_t i = 0; i < n; i++) {
+            re_im[2 * i * stride]     = tmp[2 * i];
+            re_im[2 * i * stride + 1] = tmp[2 * i + 1];
+        }
+        return;
+    }
     int lg = 0;
     while ((1LL << lg) < n) lg++;
     for (int64_t i = 0; i < n; i++) {
@@ -758,7 +777,7 @@ int zo_run(const zo_config *cfg, int nrows, const double *ks, const double *ps, 
            unsigned char *records, double *stats) {
     const int64_t N = cfg->ppd;
     const int na    = zo_narray(cfg);
-    if (N & (N - 1)) return 1;
+    if (N & 1) return 1;
     double *cube = (double *) malloc(sizeof(double) * 2 * na * N * N * N);
     if (!cube) return 2;
     zo_spectral_cube(cfg, nrows, ks, ps, eig_ppd, eig, cube);
@@ -785,7 +804,7 @@ int zo_planes(const zo_config *cfg, int nrows, const double *ks, const double *p
               const int64_t *zs, unsigned char *records, double *stats) {
     const int64_t N = cfg->ppd, M = 65536, half = N / 2;
     const int na = zo_narray(cfg);
-    if ((N & (N - 1)) || cfg->f_NL != 0. || nplanes < 1 || nplanes > 16) return 1;
+    if ((N & 1) || cfg->f_NL != 0. || nplanes < 1 || nplanes > 16) return 1;
     for (int p = 0; p < nplanes; p++)
         if (zs[p] < 0 || zs[p] >= N) return 1;
     zo_state st;

@@ -49,6 +49,9 @@ CASES = {
     "za16_fnl_rvdouble": (dict(NP=16**3, ICFormat='"RVdoubleZel"', ZD_f_NL="5000", ZD_n_s="0.96", Omega_M="0.3"), None),
     "plt16_fnl_rvzel": (dict(NP=16**3, ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="5.0", ICFormat='"RVZel"', ZD_f_NL="-2000",
                              ZD_n_s="0.96", Omega_M="0.3"), 8),
+    # non-power-of-two particle grids (the reference takes any even ppd: src/block_array.cpp:38-40; its shim FFT sums them directly)
+    "za24_rvdouble": (dict(NP=24**3, ICFormat='"RVdoubleZel"', ZD_NumBlock=2), None),
+    "plt48_rvzel": (dict(NP=48**3, ZD_qPLT=1, ZD_qPLT_rescale=1, ZD_PLT_target_z="5.0", ICFormat='"RVZel"', ZD_NumBlock=4, CPD=7), 16),
 }
 
 

@@ -441,10 +441,60 @@ def test_cli_matches_reference_layout(pkg, oracle):
 
 def test_errors_are_reported(pkg):
     with pytest.raises(pkg.ZpltError):
-        pkg.Context(pkg.make_config(48))  # not a power of two
+        pkg.Context(pkg.make_config(45))  # odd: the reference asserts an even ppd (src/block_array.cpp:38)
+    with pytest.raises(pkg.ZpltError):
+        pkg.Context(pkg.make_config(1536))  # not a power of two and beyond the general path's range
     ctx = pkg.Context(pkg.make_config(32))
     with pytest.raises(pkg.ZpltError):
         ctx.generate()  # power spectrum not set
+    ctx.close()
+
+
+# ---------------------------------------------------------------- ppd not a power of two
+@pytest.mark.parametrize("case", [
+    dict(ppd=24, icformat="RVZel"),
+    dict(ppd=80, k_cutoff=2.0, corner_modes=1, icformat="Zeldovich", seed=-11),
+    dict(ppd=96, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, f_cluster=0.97, icformat="RVdoubleZel", eig=128),
+    dict(ppd=48, qPLT=1, icformat="RVZel", eig=16),
+    dict(ppd=20, icformat="ZelSimple"),
+])
+def test_general_ppd_full_path(pkg, oracle, case):
+    """Even ppd that is not a power of two (the reference takes any even ppd, src/block_array.cpp:38-40; its production
+    grids are 2^a 3^b): the general path — plain generation kernel, Bluestein transforms on the power-of-two kernels, unfused
+    emission — against the oracle (direct DFT).  Same bars as everywhere: ids exact, fields 1e-10 / one float ulp."""
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    got_spec = ctx.spectral()
+    want_spec = oracle.spectral_cube(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    assert np.max(np.abs(got_spec - want_spec)) / np.max(np.abs(want_spec)) < 1e-13
+    ctx.generate()
+    got = ctx.fetch_planes(0, kw["ppd"])
+    want, wst = oracle.run(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    worst = compare_records(oracle, got, want)
+    st = ctx.stats()
+    assert abs(st["density_variance"] / wst["density_variance"] - 1) < 1e-10
+    assert np.allclose(st["max_disp"], wst["max_disp"], rtol=1e-10)
+    print(case, "worst field-relative error", worst)
+    ctx.close()
+
+
+def test_general_ppd_768_planes(pkg, oracle):
+    """ppd = 768 = 2^8 * 3 (an Abacus-style grid) with qPLT + rescale, RVZel: planes against the plane oracle."""
+    import torch
+
+    if torch.cuda.mem_get_info()[0] < (40 << 30):
+        pytest.skip("needs ~30 GB of free device memory")
+    kw = default_kw(ppd=768, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel")
+    synth = load_synth()
+    eig = (128, synth.make_eigmodes(128))
+    ctx, P, power = make_ctx(pkg, kw, helpers.wmap_pk(), eig)
+    ctx.generate()
+    worst = plane_check(pkg, oracle, ctx, kw, eig, [0, 383, 767])
+    print("ppd=768 worst field-relative error", worst)
     ctx.close()
 
 

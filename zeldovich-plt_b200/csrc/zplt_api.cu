@@ -116,6 +116,10 @@ struct zplt_ctx {
     cudaEvent_t ev_emit[2 * ZPLT_MAX_EMIT_EVENTS];
     int n_emit_ev;
     int launches[4];
+    // ppd not a power of two: Bluestein length, chirp, transformed conjugate chirp, work array [M][Qb]
+    int blu_M;
+    cplx *blu_w, *blu_B, *blu_W;
+    long long blu_Qb;
     unsigned int *group_flags;  // [32]: [j] set when the generation kernel of row group j has completed (resident z pass), [31] = time-out marker
     Tuning tn;     // switches: environment defaults read once in zplt_create, zplt_set_option afterwards
     LaunchRes lr;  // work counters of the persistent kernels, SM count
@@ -192,8 +196,13 @@ extern "C" int zplt_create(const zplt_config *cfg, zplt_ctx **out) {
 
 static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partial) {
     const long long N = cfg->ppd;
-    if (N < 16 || N > 2048 || (N & (N - 1)))
-        return fail(ZPLT_EINVAL, "ppd=%lld unsupported: this build handles power-of-two ppd in [16, 2048]", N);
+    // powers of two: the fused kernels; any other even ppd (the reference's requirement, src/block_array.cpp:38-40) up to 1024:
+    // the general path of zplt_generic_kernels.cu (one GPU, no f_NL)
+    const bool pow2 = (N & (N - 1)) == 0;
+    if (N < 16 || N > 2048 || (N & 1) || (!pow2 && N > 1024))
+        return fail(ZPLT_EINVAL, "ppd=%lld unsupported: this build handles even ppd in [16, 1024] and ppd = 2048", N);
+    if (!pow2 && (cfg->nranks > 1 || cfg->f_NL != 0.))
+        return fail(ZPLT_EINVAL, "ppd=%lld is not a power of two: such grids run on one GPU and without ZD_f_NL", N);
     if (cfg->nranks > 16) return fail(ZPLT_EINVAL, "nranks=%d unsupported: at most 16 ranks (one node)", cfg->nranks);
     if (!(cfg->boxsize > 0)) return fail(ZPLT_EINVAL, "BoxSize must be positive");
     if (!(cfg->k_cutoff >= 1)) return fail(ZPLT_EINVAL, "ZD_k_cutoff must be >= 1");
@@ -311,15 +320,51 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
         g.zjump  = c->zjump;
         g.xjump  = c->xjump;
     }
-    // twiddles W_N^j = exp(+2 pi i j / N)
+    // twiddles W_L^j = exp(+2 pi i j / L), L = the length the FFT kernels run at: N, or the Bluestein length M = 2^m >= 2N-1
+    c->blu_M = 0;
+    if (!pow2) {
+        c->blu_M = 32;
+        while (c->blu_M < 2 * N - 1) c->blu_M *= 2;
+    }
     {
-        std::vector<cplx> tw(N);
-        for (long long j = 0; j < N; j++) {
-            long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double) j / (long double) N;
+        const long long L = pow2 ? N : c->blu_M;
+        const long double PI = 3.14159265358979323846264338327950288L;
+        std::vector<cplx> tw(L);
+        for (long long j = 0; j < L; j++) {
+            long double ang = 2.0L * PI * (long double) j / (long double) L;
             tw[j]           = make_double2((double) cosl(ang), (double) sinl(ang));
         }
         int rc;
         if ((rc = upload((void **) &c->tw, tw.data(), tw.size() * sizeof(cplx), c->stream))) return rc;
+        if (!pow2) {
+            // chirp w[n] = exp(+i pi n^2 / N) with the phase reduced exactly (n^2 mod 2N), and Bhat = the length-M backward transform
+            // of b[m] = conj(w[|m|]) (|m| < N, wrapped), summed directly in long double: M^2 = 4 M terms at most, once per context
+            const long long M = c->blu_M;
+            std::vector<cplx> w(N), Bh(M);
+            std::vector<long double> br(M, 0.0L), bi(M, 0.0L), tr(M), ti(M);
+            for (long long n = 0; n < N; n++) {
+                const long double ang = PI * (long double) ((n * n) % (2 * N)) / (long double) N;
+                w[n]                  = make_double2((double) cosl(ang), (double) sinl(ang));
+                br[n] = cosl(ang), bi[n] = -sinl(ang);
+                if (n) br[M - n] = br[n], bi[M - n] = bi[n];
+            }
+            for (long long j = 0; j < M; j++) {
+                const long double ang = 2.0L * PI * (long double) j / (long double) M;
+                tr[j] = cosl(ang), ti[j] = sinl(ang);
+            }
+            for (long long k = 0; k < M; k++) {
+                long double sr = 0.0L, si = 0.0L;
+                for (long long m = 0; m < M; m++) {
+                    if (br[m] == 0.0L && bi[m] == 0.0L) continue;
+                    const long long t = (m * k) % M;
+                    sr += br[m] * tr[t] - bi[m] * ti[t];
+                    si += br[m] * ti[t] + bi[m] * tr[t];
+                }
+                Bh[k] = make_double2((double) sr, (double) si);
+            }
+            if ((rc = upload((void **) &c->blu_w, w.data(), w.size() * sizeof(cplx), c->stream))) return rc;
+            if ((rc = upload((void **) &c->blu_B, Bh.data(), Bh.size() * sizeof(cplx), c->stream))) return rc;
+        }
     }
     c->ptab_count = 3LL * (N / 2) * (N / 2) + 1;
     CK(cudaMalloc((void **) &c->ptab, c->ptab_count * sizeof(double)));
@@ -354,6 +399,9 @@ extern "C" void zplt_destroy(zplt_ctx *c) {
     cudaFree(c->mtab);
     cudaFree(c->lr.counters);
     cudaFree(c->group_flags);
+    cudaFree(c->blu_w);
+    cudaFree(c->blu_B);
+    cudaFree(c->blu_W);
     for (int i = 0; i < 2; i++) {
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
         if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -644,6 +692,35 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         if ((rc = slab ? slab_potential_finish(c) : run_potential(c))) return rc;
         c->launches[0] += 10;
     }
+    if (c->blu_M) {
+        // ppd not a power of two: plain generation kernel, then every axis (x, z, y as elsewhere) by Bluestein's algorithm
+        if (!with_fft && hot) return fail(ZPLT_EINVAL, "the fused generation kernel does not exist for this ppd (not a power of two)");
+        CK(launch_generate(c->gp, c->cube, c->stream));
+        c->launches[0] += 1;
+        CK(cudaEventRecord(c->ev_gen[1], c->stream));
+        if (with_fft) {
+            if (!c->blu_W) {
+                const int T = fft_tile_T(c->blu_M);
+                long long Qb = (256ll << 20) / ((long long) c->blu_M * (long long) sizeof(cplx));  // a 256 MB work array
+                const long long total = (long long) c->na * c->N * c->N;
+                if (Qb > total) Qb = total;
+                Qb = (Qb + T - 1) / T * T;
+                CK(cudaMalloc((void **) &c->blu_W, (size_t) Qb * c->blu_M * sizeof(cplx)));
+                c->blu_Qb = Qb;
+            }
+            const int axes[3] = {0, 2, 1};
+            for (int i = 0; i < 3; i++)
+                CK(launch_bluestein_axis(c->cube, c->N, c->blu_M, c->na, axes[i], c->blu_W, c->blu_Qb, c->blu_w, c->blu_B, c->tw, c->tn, c->lr,
+                                         c->stream));
+            c->launches[1] += 15;
+        }
+        CK(cudaEventRecord(c->ev_gen[2], c->stream));
+        CK(cudaEventRecord(c->ev_gen[3], c->stream));
+        c->n_emit_ev = 0;
+        c->generated = with_fft;
+        c->exchanged = false;
+        return ZPLT_OK;
+    }
     const int gt = (with_fft || hot) ? gen_xfft_T(c->N, c->na) : 0;
     if (slab && c->p2p) {
         // Slab rank with mapped peers: stage 1 runs in groups of rows.  The z pass of group j (NVLink-bound,
@@ -779,8 +856,13 @@ extern "C" int zplt_emit_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, voi
     }
     bool timed = c->n_emit_ev < ZPLT_MAX_EMIT_EVENTS;
     if (timed) CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev], c->stream));
-    CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->sg.G > 1 ? c->cube + c->slab_elems : c->cube, c->sg, z0, nz, ep, c->tw,
-                               c->tn, c->lr, c->stream, &c->launches[3]));
+    if (c->blu_M) {  // ppd not a power of two: the cube is fully transformed, emission is its own kernel
+        CK(launch_emit_plain(c->cube, c->N, z0, nz, ep, c->stream));
+        c->launches[3] += 1;
+    } else {
+        CK(launch_fft_emit_strided(c->N, fft_tile_T(c->N), c->sg.G > 1 ? c->cube + c->slab_elems : c->cube, c->sg, z0, nz, ep, c->tw,
+                                   c->tn, c->lr, c->stream, &c->launches[3]));
+    }
     if (timed) {
         CK(cudaEventRecord(c->ev_emit[2 * c->n_emit_ev + 1], c->stream));
         c->n_emit_ev++;

@@ -109,6 +109,12 @@ int launch_fft2048_emit(const cplx *planes, long long z_first, long long nz, con
 int launch_fft_emit_strided(int N, int T, const cplx *cube, const SlabGeom &sg, long long z_first, long long nz,
                             const EmitParams &ep, const cplx *tw, const Tuning &tn, LaunchRes &lr, cudaStream_t st, int *launches);
 
+// ppd not a power of two (zplt_generic_kernels.cu): one axis of the cube through Bluestein's algorithm on the length-M kernels
+// (W = work array [M][Qb], w = chirp exp(i pi n^2/N), Bhat = transform of the conjugate chirp, twM = W_M table), unfused emission
+int launch_bluestein_axis(cplx *cube, int N, int M, int na, int axis, cplx *W, long long Qb, const cplx *w, const cplx *Bhat,
+                          const cplx *twM, const Tuning &tn, LaunchRes &lr, cudaStream_t st);
+int launch_emit_plain(const cplx *cube, int N, long long z_first, long long nz, const EmitParams &ep, cudaStream_t st);
+
 int launch_power_table(double *ptab, long long count, double fundamental2, int is_powerlaw, double index, int n,
                        const double *x, const double *y, const double *y2, double normalization, double smooth2,
                        cudaStream_t st);
