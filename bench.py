@@ -259,8 +259,8 @@ def main_reference(args, rank, world):
     qplt = not args.za
     threads = os.cpu_count() or 1
     ppd, why = ref_ppd_for(args, qplt)
-    # a step of the reference at PPD=1024 is ~half a minute of all host cores: bound the arm to a few minutes
-    budget_s = 200.0
+    # a step of the reference at PPD=1024 is ~half a minute of all host cores: bound the arm to ~2-3 minutes
+    budget_s = 120.0
     times, last, nwarm = [], None, 0
     t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
