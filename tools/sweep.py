@@ -22,12 +22,12 @@ from __graft_entry__ import PKG_DIR, load_package, load_synth  # noqa: E402
 
 VARIANTS = {
     "default": {},
-    "ctas40": {"p2p_ctas": 40},
-    "ctas56": {"p2p_ctas": 56},
-    "ctas64": {"p2p_ctas": 64},
-    "no helper": {"p2p_helper": 0},
-    "per-group launches, 64 CTAs": {"p2p_resident": 0, "p2p_ctas": 64},
-    "per-group launches, 96 CTAs, 8 groups, no ring (round 1)": {"p2p_resident": 0, "slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
+    "per-source receive layout": {"b2_layout": 1},
+    "pad 8": {"b2_pad": 8},
+    "pad 520": {"b2_pad": 520},
+    "pad 4104": {"b2_pad": 4104},
+    "per-source, per-group launches, 96 CTAs, 8 groups, no ring (round 1)": {"b2_layout": 1, "p2p_resident": 0, "slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
+    "default again": {},
 }
 VARIANTS_2048 = {
     "default": {},
@@ -36,7 +36,7 @@ VARIANTS_2048 = {
     "ctas98": {"p2p_ctas": 98},
     "per-group launches, 96 CTAs": {"p2p_resident": 0, "p2p_ctas": 96},
 }
-DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1}
+DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1, "b2_layout": 0, "b2_pad": 0}
 
 
 def main():

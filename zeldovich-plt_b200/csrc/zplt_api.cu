@@ -75,6 +75,7 @@ struct zplt_ctx {
     GenParams gp;
     SlabGeom sg;
     size_t slab_elems;  // complex elements of one slab buffer
+    size_t b2_elems;    // complex elements of the receive buffer (slab_elems + room for padded planes)
     size_t phi_elems;   // slab rank with ZD_f_NL: complex elements of one buffer of the potential pass (else 0)
     int phi_stage;      // slab rank with ZD_f_NL: 0 = nothing, 1 = zplt_potential_begin done, 2 = zplt_potential_exchange done
     bool exchanged;
@@ -132,7 +133,7 @@ static void tuning_from_env(Tuning &t) {
         int *v;
     } tab[] = {{"ZPLT_ZRING", &t.zring},           {"ZPLT_YRING", &t.yring},           {"ZPLT_WIDE_RECORDS", &t.wide_records},
                {"ZPLT_EMIT_SCRATCH", &t.emit_scratch}, {"ZPLT_EMIT_PREFETCH", &t.emit_prefetch}, {"ZPLT_SLAB_GROUPS", &t.slab_groups},
-               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring}, {"ZPLT_P2P_RESIDENT", &t.p2p_resident}, {"ZPLT_P2P_HELPER", &t.p2p_helper},
+               {"ZPLT_P2P_CTAS", &t.p2p_ctas},     {"ZPLT_DIT2048", &t.dit2048},       {"ZPLT_DIT2048_EMIT", &t.dit2048_emit},       {"ZPLT_SLAB_RING", &t.slab_ring}, {"ZPLT_P2P_RESIDENT", &t.p2p_resident}, {"ZPLT_P2P_HELPER", &t.p2p_helper}, {"ZPLT_B2_LAYOUT", &t.b2_layout}, {"ZPLT_B2_PAD", &t.b2_pad},
                {"ZPLT_GEN_PERSIST", &t.gen_persist}};
     for (auto &e : tab) {
         const char *s = getenv(e.name);
@@ -148,7 +149,7 @@ extern "C" int zplt_set_option(zplt_ctx *c, const char *name, int32_t value) {
         int *v;
     } tab[] = {{"zring", &t.zring},           {"yring", &t.yring},           {"wide_records", &t.wide_records},
                {"emit_scratch", &t.emit_scratch}, {"emit_prefetch", &t.emit_prefetch}, {"slab_groups", &t.slab_groups},
-               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring}, {"p2p_resident", &t.p2p_resident}, {"p2p_helper", &t.p2p_helper},
+               {"p2p_ctas", &t.p2p_ctas},     {"dit2048", &t.dit2048},       {"dit2048_emit", &t.dit2048_emit},       {"slab_ring", &t.slab_ring}, {"p2p_resident", &t.p2p_resident}, {"p2p_helper", &t.p2p_helper}, {"b2_layout", &t.b2_layout}, {"b2_pad", &t.b2_pad},
                {"gen_persist", &t.gen_persist}};
     for (auto &e : tab)
         if (!strcmp(e.name, name)) {
@@ -266,7 +267,10 @@ static int create_impl(const zplt_config *cfg, zplt_ctx **out, zplt_ctx **partia
     // two buffers of the potential pass (this rank's rows [z][slot][x], this rank's planes [zl][y][x]), inside the same
     // allocation so that one IPC handle maps everything a peer stores into
     c->phi_elems  = (cfg->nranks > 1 && cfg->f_NL != 0.) ? (size_t) N * N * N / cfg->nranks : 0;
-    c->cube_bytes = (c->slab_elems * (cfg->nranks > 1 ? 2 : 1) + 2 * c->phi_elems) * sizeof(cplx);
+    // the receive buffer can be laid out with padded planes (Tuning::b2_pad): room for the largest padding
+    c->b2_elems   = cfg->nranks > 1 ? c->slab_elems + (size_t) (N / cfg->nranks) * ZPLT_B2_PAD_MAX : 0;
+    c->cube_bytes = (c->slab_elems + c->b2_elems + 2 * c->phi_elems) * sizeof(cplx);
+    c->sg.b2_zstride = (long long) c->na * N * N, c->sg.b2_persrc = 0;
 
     // derived scalars, written exactly as the reference computes them
     GenParams &g  = c->gp;
@@ -573,8 +577,8 @@ static int run_potential(zplt_ctx *c) {
 // ---- ZD_f_NL on slab ranks: the same pass with its two transposes (reference ZeldovichZ gen_phi + ZeldovichXY_Phi with
 // StoreBlock/LoadBlock and StoreBlockForward/LoadBlockForward, src/zeldovich.cpp:699-790, src/block_array.cpp:305-464) ----
 // buffers behind the two slab buffers: P1 = this rank's rows [z][slot][x], P2 = this rank's planes [zl][y][x]
-static cplx *phi_p1(zplt_ctx *c) { return c->cube + 2 * c->slab_elems; }
-static cplx *phi_p2(zplt_ctx *c) { return c->cube + 2 * c->slab_elems + c->phi_elems; }
+static cplx *phi_p1(zplt_ctx *c) { return c->cube + c->slab_elems + c->b2_elems; }
+static cplx *phi_p2(zplt_ctx *c) { return c->cube + c->slab_elems + c->b2_elems + c->phi_elems; }
 
 static TileGeom rows_geom(int N, int T, long long nrows_per_block, long long nblocks, long long block_stride) {
     // contiguous rows of N points: nblocks blocks of nrows_per_block consecutive rows, block_stride elements apart
@@ -609,8 +613,9 @@ extern "C" int zplt_potential_begin(zplt_ctx *c) {
     CK(launch_fft_tiles_any(N, T, P1, rows_geom(N, T, (long long) N * 2 * h, 1, 0), c->tw, c->tn, c->lr, c->stream));
     SlabGeom s1 = c->sg;
     s1.na = 1, s1.ly0 = 0, s1.nly = h;
+    s1.b2_zstride = (long long) N * N, s1.b2_persrc = 0;  // the potential's planes: [zl][y][x]
     cplx *peers[16];
-    for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->slab_elems + c->phi_elems : nullptr;
+    for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->b2_elems + c->phi_elems : nullptr;
     Tuning tn   = c->tn;
     tn.p2p_ctas = 0;  // nothing runs beside it
     CK(launch_fft_tiles_p2p_any(N, T, P1, s1, peers, c->tw, tn, c->lr, GroupSync{nullptr, c->group_flags + 31, 1, nullptr}, c->stream));
@@ -635,7 +640,7 @@ extern "C" int zplt_potential_exchange(zplt_ctx *c) {
     // x transform of the rows that are read back: y < N/2 of every plane
     CK(launch_fft_tiles_any(N, T, P2, rows_geom(N, T, N / 2, np, (long long) N * N), c->tw, c->tn, c->lr, c->stream));
     cplx *peers[16];
-    for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->slab_elems : nullptr;
+    for (int r = 0; r < 16; r++) peers[r] = (r < c->sg.G && c->peer_recv[r]) ? c->peer_recv[r] + c->b2_elems : nullptr;
     CK(launch_phi_return(P2, c->sg, peers, c->stream));
     c->phi_stage = 2;
     return ZPLT_OK;
@@ -736,6 +741,13 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         // group j once flags[j] is set (a stream-ordered memset after the generation kernel of group j).  Launched per group
         // instead (p2p_resident = 0), its CTAs have to win whole SMs back from two-per-SM generation CTAs and mostly run after
         // them: measured on 8 GPUs at PPD=1024, generation done after 8.0 ms, z pass only after 14.7 ms (link time ~11 ms).
+        // receive layout of this step (the emission below reads what is chosen here)
+        {
+            int pad = c->tn.b2_pad < 0 ? 0 : (c->tn.b2_pad > ZPLT_B2_PAD_MAX ? ZPLT_B2_PAD_MAX : c->tn.b2_pad);
+            pad &= ~7;  // whole 128-byte rows
+            c->sg.b2_persrc  = c->tn.b2_layout == 1;
+            c->sg.b2_zstride = (long long) c->na * c->N * c->N + pad;
+        }
         SlabGeom sg = c->sg;
         sg.nly      = c->sg.h / J;
         const int T = fft_tile_T(c->N);
@@ -849,8 +861,8 @@ extern "C" int zplt_emit_planes_density(zplt_ctx *c, int64_t z0, int64_t nz, voi
     const long long N2 = (long long) c->N * c->N;
     if (c->sg.G == 1) {  // the cube [a][z][y][x]
         ep.astride = N2 * c->N, ep.zstride = N2, ep.zglobal0 = 0, ep.nzl = c->N;
-    } else if (c->p2p) {  // after the fused exchange: [zl][a][y][x], rows at their true y
-        ep.astride = N2, ep.zstride = N2 * c->na, ep.zglobal0 = (long long) c->sg.rank * nplanes, ep.nzl = nplanes;
+    } else if (c->p2p && !c->sg.b2_persrc) {  // after the fused exchange: [zl][a][y][x], rows at their true y
+        ep.astride = N2, ep.zstride = c->sg.b2_zstride, ep.zglobal0 = (long long) c->sg.rank * nplanes, ep.nzl = nplanes;
     } else {  // after a caller-run all-to-all: per-source blocks B2[src][zl][a][slot][x] (zplt_slab.h)
         ep.astride = 0, ep.zstride = 0, ep.zglobal0 = (long long) c->sg.rank * nplanes, ep.nzl = nplanes;
     }
@@ -1027,6 +1039,7 @@ extern "C" int64_t zplt_slab_offset(int64_t ppd, int32_t nranks, int32_t narray,
     g.log2G = 0;
     while ((1 << g.log2G) < g.G) g.log2G++;
     g.ly0 = 0, g.nly = g.h;
+    g.b2_zstride = 0, g.b2_persrc = 1;
     if (stage == 1) {  // where rank `rank` (the owner of row y) keeps row (a, z, y) before the exchange
         int r, s;
         slab_owner(g.N, g.G, (int) y, r, s);

@@ -163,7 +163,6 @@ __global__ void __launch_bounds__(512, 1)
     const long long nstride = (long long) rows * N;
     const int np  = N / sg.G, lognp = 11 - sg.log2G;
     const int nsl = 2 * sg.nly;
-    const int na  = sg.na;
     const long long tpg = (long long) XT * nsl * sg.na, ntiles = tpg * gs.J;  // tiles are numbered group by group (see p2p_tile)
     int ready = gs.flags == nullptr ? gs.J : -1;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -186,7 +185,8 @@ __global__ void __launch_bounds__(512, 1)
         const int x    = xt * T + p;
         const int y    = slab_row(N, sg.G, sg.rank, slot);
         const long long base = (long long) row * N + x;
-        const long long rowoff = ((long long) a * N + y) * N + x, zstride = (long long) na * N * N;
+        const long long zstride = sg.b2_persrc ? (long long) rows * N : sg.b2_zstride;
+        const long long rowoff  = sg.b2_persrc ? ((long long) sg.rank * np * rows + row) * N + x : ((long long) a * N + y) * N + x;
         // planes k and k + 1024 have the same local index on ranks G/2 apart (N/G divides 1024 for G >= 2)
         const int rhalf = sg.G >> 1;
         dit2048_tile(b1, base, nstride, S + p * Split::PSTRIDE, park, tw, tid, b, [&](int k, cplx lo, cplx hi) {

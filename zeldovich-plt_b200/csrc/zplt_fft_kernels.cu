@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(T *(N / 16), min_ctas(T *(N / 16)))
         const int x    = xt * T + p;
         const int y    = slab_row(N, sg.G, sg.rank, slot);
         const long long base = (long long) row * N + x;
-        const long long rowoff = ((long long) a * N + y) * N + x, zstride = (long long) sg.na * N * N;  // B2[zl][a][y][x]
+        // where the rows of this tile land in an owner's buffer: plane zl at zl*zstride + rowoff
+        const long long zstride = sg.b2_persrc ? (long long) rows * N : sg.b2_zstride;
+        const long long rowoff  = sg.b2_persrc ? ((long long) sg.rank * np * rows + row) * N + x : ((long long) a * N + y) * N + x;
         cplx v[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);
@@ -398,7 +400,9 @@ __global__ void __launch_bounds__(T *(N / 16), 1)
         const int x   = xt * T + p;
         const int y   = slab_row(N, sg.G, sg.rank, slot);
         const long long base = (long long) row * N + x;
-        const long long rowoff = ((long long) a * N + y) * N + x, zstride = (long long) sg.na * N * N;  // B2[zl][a][y][x]
+        // where the rows of this tile land in an owner's buffer: plane zl at zl*zstride + rowoff
+        const long long zstride = sg.b2_persrc ? (long long) rows * N : sg.b2_zstride;
+        const long long rowoff  = sg.b2_persrc ? ((long long) sg.rank * np * rows + row) * N + x : ((long long) a * N + y) * N + x;
         cplx v[16];
 #pragma unroll
         for (int e = KP; e < 16; e++) v[e] = ld_stream(&b1[base + (long long) (b + M * e) * nstride]);

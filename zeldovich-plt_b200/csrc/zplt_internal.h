@@ -40,6 +40,7 @@ struct EmitParams {
     int nzl;            // local planes held
 };
 #define ZPLT_STAT_SLOTS 64
+#define ZPLT_B2_PAD_MAX 8192
 // EmitParams::scratch: [256 SMs][16][512 threads] x 24 B of record parking, then [256 SMs] x 64 KB that replace the
 // shared-memory parking area in the persistent ring emission kernel
 #define ZPLT_SCRATCH_PARK_BYTES ((size_t) 256 * 16 * 512 * 24)
@@ -60,6 +61,8 @@ struct Tuning {
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
     int p2p_resident = 1;   // ZPLT_P2P_RESIDENT: one z pass + exchange launch for the whole of stage 1, gated by per-group flags
+    int b2_layout    = 0;   // ZPLT_B2_LAYOUT: receive layout of the fused exchange: 0 = rows at their true y, 1 = per-source blocks
+    int b2_pad       = 0;   // ZPLT_B2_PAD: complex elements added to the plane stride of layout 0 (<= ZPLT_B2_PAD_MAX)
     int p2p_helper   = 1;   // ZPLT_P2P_HELPER: a second launch of it on the SMs the generation kernels leave behind when they are done
     int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
 };

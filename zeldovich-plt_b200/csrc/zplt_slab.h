@@ -42,6 +42,11 @@ struct SlabGeom {
     // stage 1 can run in groups of primary rows [ly0, ly0+nly) (and their partners' slots
     // h+ly0 ...), so that generating one group overlaps with sending the previous one
     int ly0, nly;
+    // receive layout of the fused exchange (the sender computes every address, so it is a choice): rows at their true y,
+    // [zl][a][y][x] with b2_zstride elements between planes (>= na*N*N: padding breaks the power-of-two plane stride), or
+    // (b2_persrc) the per-source blocks [src][zl][a][slot][x] of the caller-run all-to-all
+    long long b2_zstride;
+    int b2_persrc;
 };
 
 // which rank owns row y, and in which of its 2h slots
