@@ -21,22 +21,19 @@ import bench  # noqa: E402
 from __graft_entry__ import PKG_DIR, load_package, load_synth  # noqa: E402
 
 VARIANTS = {
-    "default": {},
-    "per-source receive layout": {"b2_layout": 1},
-    "pad 8": {"b2_pad": 8},
-    "pad 520": {"b2_pad": 520},
-    "pad 4104": {"b2_pad": 4104},
-    "per-source, per-group launches, 96 CTAs, 8 groups, no ring (round 1)": {"b2_layout": 1, "p2p_resident": 0, "slab_groups": 8, "p2p_ctas": 96, "slab_ring": 0},
-    "default again": {},
+    "default (per-source receive layout)": {},
+    "rows at their true y": {"b2_layout": 0},
+    "rows at their true y, pad 4104": {"b2_layout": 0, "b2_pad": 4104},
+    "per-source, 96 CTAs": {"p2p_ctas": 96},
+    "per-source, per-group launches": {"p2p_resident": 0},
 }
 VARIANTS_2048 = {
-    "default": {},
-    "ctas56": {"p2p_ctas": 56},
-    "ctas84": {"p2p_ctas": 84},
-    "ctas98": {"p2p_ctas": 98},
-    "per-group launches, 96 CTAs": {"p2p_resident": 0, "p2p_ctas": 96},
+    "default (per-source receive layout)": {},
+    "rows at their true y": {"b2_layout": 0},
+    "per-source, 64 CTAs": {"p2p_ctas": 64},
+    "per-source, 98 CTAs": {"p2p_ctas": 98},
 }
-DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1, "b2_layout": 0, "b2_pad": 0}
+DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1, "b2_layout": 1, "b2_pad": 0}
 
 
 def main():

@@ -61,7 +61,9 @@ struct Tuning {
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
     int p2p_resident = 1;   // ZPLT_P2P_RESIDENT: one z pass + exchange launch for the whole of stage 1, gated by per-group flags
-    int b2_layout    = 0;   // ZPLT_B2_LAYOUT: receive layout of the fused exchange: 0 = rows at their true y, 1 = per-source blocks
+    int b2_layout    = 1;   // ZPLT_B2_LAYOUT: receive layout of the fused exchange: 0 = rows at their true y, 1 = per-source blocks
+                            // (4 GPUs, PPD=1024: stage 1 26.0 ms / 495 GB/s per GPU with 0, 19.5 ms / 662 GB/s with 1; the y pass
+                            // pays 1.4 ms for it — profiles/r02_sweep_4gpu_receive_layout.jsonl)
     int b2_pad       = 0;   // ZPLT_B2_PAD: complex elements added to the plane stride of layout 0 (<= ZPLT_B2_PAD_MAX)
     int p2p_helper   = 1;   // ZPLT_P2P_HELPER: a second launch of it on the SMs the generation kernels leave behind when they are done
     int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
