@@ -556,6 +556,8 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     (4, {"slab_ring": 2}, dict(ppd=512, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
     # receive layouts of the fused exchange: per-source blocks, padded planes
     (4, {"b2_layout": 1}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    (4, {"b2_layout": 0}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),
+    (2, {"b2_layout": 1}, dict(ppd=128, qPLT=1, icformat="RVdoubleZel", eig=16)),
     (8, {"b2_pad": 520}, dict(ppd=256, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=128)),
     (2, {"b2_pad": 8192, "p2p_resident": 0}, dict(ppd=128, icformat="RVZel")),
     (2, {"slab_groups": 1, "p2p_ctas": 0}, dict(ppd=128, k_cutoff=2.0, icformat="Zeldovich")),

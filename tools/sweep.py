@@ -33,7 +33,7 @@ VARIANTS_2048 = {
     "per-source, 64 CTAs": {"p2p_ctas": 64},
     "per-source, 98 CTAs": {"p2p_ctas": 98},
 }
-DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1, "b2_layout": 1, "b2_pad": 0}
+DEFAULTS = {"p2p_ctas": -1, "slab_groups": 16, "slab_ring": 1, "dit2048": 1, "dit2048_emit": 0, "p2p_resident": 1, "p2p_helper": 1, "b2_layout": -1, "b2_pad": 0}
 
 
 def main():

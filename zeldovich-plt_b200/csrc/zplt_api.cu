@@ -745,7 +745,7 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         {
             int pad = c->tn.b2_pad < 0 ? 0 : (c->tn.b2_pad > ZPLT_B2_PAD_MAX ? ZPLT_B2_PAD_MAX : c->tn.b2_pad);
             pad &= ~7;  // whole 128-byte rows
-            c->sg.b2_persrc  = c->tn.b2_layout == 1;
+            c->sg.b2_persrc  = c->tn.b2_layout < 0 ? (c->sg.G >= 4 && c->N <= 1024) : c->tn.b2_layout == 1;
             c->sg.b2_zstride = (long long) c->na * c->N * c->N + pad;
         }
         SlabGeom sg = c->sg;

@@ -61,9 +61,11 @@ struct Tuning {
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
     int slab_ring    = 1;   // ZPLT_SLAB_RING: ring-prefetched forms of the slab-rank kernels
     int p2p_resident = 1;   // ZPLT_P2P_RESIDENT: one z pass + exchange launch for the whole of stage 1, gated by per-group flags
-    int b2_layout    = 1;   // ZPLT_B2_LAYOUT: receive layout of the fused exchange: 0 = rows at their true y, 1 = per-source blocks
-                            // (4 GPUs, PPD=1024: stage 1 26.0 ms / 495 GB/s per GPU with 0, 19.5 ms / 662 GB/s with 1; the y pass
-                            // pays 1.4 ms for it — profiles/r02_sweep_4gpu_receive_layout.jsonl)
+    int b2_layout    = -1;  // ZPLT_B2_LAYOUT: receive layout of the fused exchange: 0 = rows at their true y, 1 = per-source blocks,
+                            // -1 = by measurement: per-source on >= 4 ranks up to N = 1024 (stage 1 at PPD=1024: 4 GPUs 26.0 -> 19.5 ms,
+                            // 8 GPUs 14.3 -> 11.7 ms, NVLink 495/524 -> 662/642 GB/s per GPU; the y pass pays 0.7-1.4 ms for it), rows at
+                            // their true y on 2 ranks and at N = 2048, where per-source blocks lose (8 GPUs: 195.7 vs 162.5 ms/step);
+                            // profiles/r02_sweep_{4,8}gpu_receive_layout.jsonl
     int b2_pad       = 0;   // ZPLT_B2_PAD: complex elements added to the plane stride of layout 0 (<= ZPLT_B2_PAD_MAX)
     int p2p_helper   = 1;   // ZPLT_P2P_HELPER: a second launch of it on the SMs the generation kernels leave behind when they are done
     int gen_persist  = 1;   // ZPLT_GEN_PERSIST: persistent, software-pipelined generation kernel
