@@ -524,7 +524,7 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
         ctx.synchronize()
         ctxs.append(ctx)
         bufs.append(buf)
-    half = bufs[0].numel() // 2
+    half = ctxs[0].narray * N**3 // G * 2  # float64 elements of the stage-1 buffer; the receive buffer follows it
     blk = half // G
     for dst in range(G):
         for src in range(G):
@@ -651,13 +651,14 @@ def test_c5_rank_of_eight_at_ppd2048(pkg, oracle, dit, dit_emit):
     W = torch.empty(ws // 8, dtype=torch.float64, device="cuda:0")
     open_ctxs = []
     try:
-        recv = W.data_ptr() + ws // 2
+        slab_bytes = 16 * 4 * N**3 // G  # the stage-1 buffer; the receive buffer follows it
+        recv = W.data_ptr() + slab_bytes
         zs = [0, N // G - 1, N - N // G, N - 1]
         want, _ = oracle_planes(oracle, kw, zs, eig)
         ctx0.close()
         worst = 0.0
         for target, planes in ((0, (0, 1)), (G - 1, (2, 3))):
-            W[ws // 16:].fill_(float("nan"))
+            W[slab_bytes // 8:].fill_(float("nan"))
             torch.cuda.synchronize()  # the fill runs on torch's stream, the library on its own (non-blocking) streams
             tctx = None
             for src in range(G):

@@ -29,10 +29,11 @@ class SlabWorkspace:
         self.buf = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
         ctx.set_workspace(self.buf.data_ptr(), nbytes)
         send_ptr, recv_ptr, self.bytes_per_peer = ctx.exchange_info()
-        half = self.buf.numel() // 2
+        world = dist.get_world_size()
+        half = self.bytes_per_peer * world // 8  # float64 elements of one slab buffer (the workspace may hold more behind them)
         assert send_ptr == self.buf.data_ptr() and recv_ptr == self.buf.data_ptr() + half * 8
         self.send = self.buf[:half]
-        self.recv = self.buf[half:]
+        self.recv = self.buf[half:2 * half]
 
     def begin(self):
         """Nothing to wait for: the all-to-all below is ordered on the stream after this rank's emission."""
