@@ -54,7 +54,7 @@ def main():
     ws = ctx.workspace_bytes()
     W = torch.empty(ws // 8, dtype=torch.float64, device="cuda:0")
     ctx.set_workspace(W.data_ptr(), ws)
-    recv = W.data_ptr() + ws // 2
+    recv = W.data_ptr() + 16 * ctx.narray * N**3 // G  # the receive buffer follows the stage-1 buffer
     ctx.dbg_set_peers([recv] * G)
     nloc = N // G
     rb = ctx.record_bytes
