@@ -93,6 +93,7 @@ def test_oracle_oversampling_identity(oracle):
     dict(ppd=32, k_cutoff=2.0, corner_modes=1, icformat="Zeldovich"),
     dict(ppd=16, qonemode=1, one_mode=(-3, 2, 5), icformat="ZelSimple"),
     dict(ppd=32, k_cutoff=2.0, fixed_power=1, icformat="RVdoubleZel"),
+    dict(ppd=24, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16),  # not a power of two: direct DFT sums
 ])
 def test_plane_oracle_matches_full_oracle(oracle, case):
     """zo_planes (selected planes by direct z summation — what faces the benchmark sizes) against zo_run, itself pinned to

@@ -751,7 +751,7 @@ static int run_generate(zplt_ctx *c, bool with_fft, bool hot = true) {
         SlabGeom sg = c->sg;
         sg.nly      = c->sg.h / J;
         const int T = fft_tile_T(c->N);
-        if (c->tn.p2p_ctas < 0) c->tn.p2p_ctas = c->N >= 2048 ? 84 : 64;
+        if (c->tn.p2p_ctas < 0) c->tn.p2p_ctas = c->N >= 2048 ? 84 : (c->sg.G == 2 ? 56 : 64);  // sweeps: profiles/r02_sweep_{2,8}gpu.jsonl
         if (c->tn.p2p_resident > 0) {
             sg.ly0 = 0;
             // everything that will run beside the waiting z pass must already be loaded (lazy module loading synchronises):

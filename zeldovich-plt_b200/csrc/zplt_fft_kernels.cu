@@ -264,8 +264,10 @@ __global__ void __launch_bounds__(NP *(N / 16), min_ctas(NP *(N / 16)))
 // IPC; peer[rank] is local; a NULL entry discards that rank's share: single-GPU tests of one rank).
 // This is BlockArray::StoreBlock + LoadBlock (reference src/block_array.cpp:387-414, 466-504) done by
 // the FFT epilogue, 128-byte runs.  The receiver's layout is free because the sender computes every
-// address: rows land at their true y, B2[zl][a][y][x], so stage 2 of a slab rank reads exactly what a
-// single GPU reads (the y shift of LoadBlock, :487-491, is the slot -> y map here).
+// address (SlabGeom::b2_persrc / b2_zstride): rows at their true y, B2[zl][a][y][x] — stage 2 of a slab rank then
+// reads exactly what a single GPU reads (the y shift of LoadBlock, :487-491, is the slot -> y map here) — or
+// per-source blocks B2[src][zl][a][slot][x], which sustain ~25 % more NVLink bandwidth on 4 and 8 ranks at N <= 1024
+// (DESIGN.md section 6).
 struct PeerTable {
     cplx *recv[16];
 };

@@ -55,7 +55,7 @@ struct Tuning {
     int emit_scratch = 1;   // ZPLT_EMIT_SCRATCH: park record halves in the L2-resident scratch (whole-record stores)
     int emit_prefetch = 1;  // ZPLT_EMIT_PREFETCH: L2-prefetch the next packed array of a tile (one-tile-per-CTA kernel)
     int slab_groups  = 16;  // ZPLT_SLAB_GROUPS: row groups of stage 1 on a slab rank (generation of group j+1 overlaps the z pass of j)
-    int p2p_ctas     = -1;  // ZPLT_P2P_CTAS: SMs of the z pass + exchange kernel (0 = as many as allowed, -1 = 64, or 84 at N = 2048:
+    int p2p_ctas     = -1;  // ZPLT_P2P_CTAS: SMs of the z pass + exchange kernel (0 = as many as allowed, -1 = 64 — 56 on 2 ranks, 84 at N = 2048:
                             // best of the sweeps on 8 GPUs, profiles/r02_sweep_8gpu.jsonl); generation takes the rest
     int dit2048      = 1;   // ZPLT_DIT2048: 8-pencil decimation kernels for the N = 2048 z pass (122 -> 77 ms per rank of 8, local stores)
     int dit2048_emit = 0;   // ZPLT_DIT2048_EMIT: ... and for the N = 2048 y pass + emission (measured slower than the 4-pencil kernel: 41.9 vs 33.3 ms)
