@@ -173,3 +173,38 @@ def test_cli_usage_and_bad_file(pkg):
     assert r.returncode == 1 and "Usage" in r.stderr
     r = subprocess.run([pkg.CLI_PATH, "/nonexistent.par"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1
+
+
+def test_ic_file_reader_round_trip(tmp_path):
+    """The consumer-side reader (zeldovich-plt_b200/icfiles.py) on files laid out as the reference lays them out: a golden
+    case's records split into ic_<z*CPD//PPD> files in ascending z."""
+    import importlib.util
+
+    import numpy as np
+
+    import helpers
+
+    spec = importlib.util.spec_from_file_location("zplt_icfiles", os.path.join(helpers.ROOT, "zeldovich-plt_b200", "icfiles.py"))
+    icf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(icf)
+    case, raw, _, _ = helpers.load_golden("plt16_direct_rvzel")  # CPD = 5 < PPD = 16: several planes per file
+    ppd, cpd = 16, int(case["params"]["CPD"])
+    rec = raw.view(icf.RECORD_DTYPES[1])
+    planes = icf.ic_file_planes(ppd, cpd)
+    assert sorted(planes) == sorted({z * cpd // ppd for z in range(ppd)})
+    for n, (z0, z1) in planes.items():
+        rec[z0 * ppd * ppd:z1 * ppd * ppd].tofile(str(tmp_path / f"ic_{n}"))
+    got, (z0, z1) = icf.read_ic_files(str(tmp_path), ppd, cpd, "RVZel")
+    assert (z0, z1) == (0, ppd) and np.array_equal(got.view(np.uint8), rec.view(np.uint8))
+    part, (a, b) = icf.read_ic_files(str(tmp_path), ppd, cpd, "RVZel", files=[1, 2])
+    assert np.array_equal(part["ijk"][:, 0], np.repeat(np.arange(a, b), ppd * ppd))
+    pos = icf.global_positions(got, ppd, 720.0)
+    assert pos.shape == (ppd**3, 3) and pos.min() >= 0.0 and pos.max() < 720.0
+    site = icf.lattice_indices(got, ppd) * (720.0 / ppd)
+    d = (pos - site + 360.0) % 720.0 - 360.0  # displacement back out of the wrapped position
+    assert np.allclose(d, got["displ"], atol=1e-4)
+    assert np.array_equal(icf.velocities(got), got["vel"].astype(np.float64))
+    simple = np.zeros(ppd**3, dtype=icf.RECORD_DTYPES[3])
+    assert np.array_equal(icf.lattice_indices(simple, ppd)[-1], [ppd - 1, ppd - 1, ppd - 1])
+    with pytest.raises(ValueError):
+        icf.read_ic_files(str(tmp_path), ppd + 16, cpd, "RVZel")  # wrong ppd: sizes do not match
