@@ -385,22 +385,34 @@ class Problem:
         zs = sorted({0, (world // 2) * self.nloc + min(1, self.nloc - 1), N - 1})[:max_planes]
         t0 = time.perf_counter()
         dt = self.ctx.record_dtype
+        failed = ""
         if self.rank == 0:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import zel_oracle as zo
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import zel_oracle as zo
 
-            from __graft_entry__ import load_synth
+                from __graft_entry__ import load_synth
 
-            synth = load_synth()
-            zo.set_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1 for its ranks; the other ranks only wait here
-            k, p = synth.make_power_table()
-            kw = dict(ppd=N, icformat=self.ctx.cfg.icformat)
-            if self.qplt:
-                kw.update(qPLT=1, qPLTrescale=1, PLT_target_z=5.0)
-            want, _ = zo.planes(zo.make_config(**kw), (k, p), zs, (128, synth.make_eigmodes(128)) if self.qplt else None)
-            want_t = torch.from_numpy(want.view(np.uint8).reshape(len(zs), -1).copy())
+                synth = load_synth()
+                zo.set_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1 for its ranks; the other ranks only wait here
+                k, p = synth.make_power_table()
+                kw = dict(ppd=N, icformat=self.ctx.cfg.icformat)
+                if self.qplt:
+                    kw.update(qPLT=1, qPLTrescale=1, PLT_target_z=5.0)
+                want, _ = zo.planes(zo.make_config(**kw), (k, p), zs, (128, synth.make_eigmodes(128)) if self.qplt else None)
+                want_t = torch.from_numpy(want.view(np.uint8).reshape(len(zs), -1).copy())
+            except Exception as e:  # noqa: BLE001 — the checker must not take the measurement down with it
+                failed = f"oracle unavailable: {type(e).__name__}: {e}"[:200]
+                want_t = torch.zeros((len(zs), N * N * self.rb), dtype=torch.uint8)
         else:
             want_t = torch.empty((len(zs), N * N * self.rb), dtype=torch.uint8)
+        if world > 1:
+            flag = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device=self.dev)
+            dist.broadcast(flag, src=0)
+            if flag.item() != 0.0:
+                return {"ok": None, "error": failed or "oracle unavailable on rank 0", "planes": zs}
+        elif failed:
+            return {"ok": None, "error": failed, "planes": zs}
         if world > 1:
             want_d = want_t.to(self.dev)
             dist.broadcast(want_d, src=0)
@@ -612,7 +624,15 @@ def main_b200(args, rank, world, local_rank):
             shutil.rmtree(os.path.join(tmp, "ic_files"), ignore_errors=True)
 
     # ---- BASELINE configs[4]: PPD=2048 qPLT + rescale across 8 GPUs ---------------------------
-    if world == 8 and args.exchange == "p2p" and not args.no_ppd2048 and N != 2048:
+    want2048 = world == 8 and args.exchange == "p2p" and not args.no_ppd2048 and N != 2048
+    if want2048:
+        # every rank must be able to hold its 137 GB of slabs, or none starts (a rank failing alone would leave the others waiting)
+        ok = torch.tensor([1.0 if torch.cuda.mem_get_info(dev)[0] > (150 << 30) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0.0:
+            want2048 = False
+            ppd2048 = {"error": "not every GPU has 150 GB free for the PPD=2048 slabs"}
+    if want2048:
         try:
             pb2 = Problem(pkg, synth, zd, torch, dist, args, 2048, True, rank, world, local_rank, dev, tmp)
             ms2, a2a2, st2, _ = pb2.measure(3, 2)

@@ -208,3 +208,35 @@ def test_ic_file_reader_round_trip(tmp_path):
     assert np.array_equal(icf.lattice_indices(simple, ppd)[-1], [ppd - 1, ppd - 1, ppd - 1])
     with pytest.raises(ValueError):
         icf.read_ic_files(str(tmp_path), ppd + 16, cpd, "RVZel")  # wrong ppd: sizes do not match
+
+
+def test_density_file_name_formatting(pkg):
+    """ZD_density_filename goes through fmt::format(name, ppd) in the reference (src/output.cpp:283)."""
+    f = pkg.format_density_name
+    assert f("density{:d}", 256) == "density256"
+    assert f("density{}", 64) == "density64" and f("d{0}.bin", 64) == "d64.bin" and f("d{0:d}", 7) == "d7"
+    assert f("rho_{:05d}.f32", 128) == "rho_00128.f32" and f("rho_{:5d}", 128) == "rho_  128"
+    assert f("plain", 32) == "plain" and f("{{x}}{:d}", 32) == "{x}32"
+
+
+def test_bench_line_helpers():
+    """The pure parts of bench.py (roofline block, workload description, reference sample size) on CPU."""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("zplt_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, na, rb = 1024, 4, 32
+    r = bench.roofline_block(N, na, rb, 1, [30.5, 27.5, 24.9], 82.9, False)
+    assert r["kernel"].startswith("gen_xfft_kernel") and set(r["kernels"]) == set(bench.KERNELS)
+    assert abs(r["kernels"]["z-FFT"]["achieved"] - 32 * na * N**3 / 27.5e-3 / 1e9) < 1e-6
+    assert abs(r["step_algorithmic_bytes"] - (64 * na + rb) * N**3) == 0 and 0.5 < r["step_frac"] < 0.65
+    r8 = bench.roofline_block(N, na, rb, 8, [8.0, 3.7, 4.0], 15.9, True)
+    assert set(r8["kernels"]) == {"generate+x-FFT", "y-FFT+emit"} and abs(r8["kernels"]["generate+x-FFT"]["ms"] - 11.7) < 1e-9
+    cfg = bench.workload_config(N, True, "RVZel", 8, "p2p")
+    assert cfg["ppd"] == N and cfg["narray"] == 4 and "8 GPUs" in cfg["parallelism"]
+    args = argparse.Namespace(ref_ppd=0, ppd=1024)
+    ppd, why = bench.ref_ppd_for(args, True)
+    assert ppd in (128, 256, 512, 1024) and why
+    assert bench.ref_ppd_for(argparse.Namespace(ref_ppd=256, ppd=1024), True)[0] == 256

@@ -489,6 +489,15 @@ def fft_backward(data, row_mode=True, variant=0):
     return a
 
 
+def format_density_name(pattern, ppd):
+    """ZD_density_filename with ppd filled in, as the reference's fmt::format does it (src/output.cpp:283)."""
+    L = lib()
+    L.zplt_format_density_name_.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p, C.c_size_t]
+    buf = C.create_string_buffer(2048)
+    L.zplt_format_density_name_(pattern.encode(), int(ppd), buf, 2048)
+    return buf.value.decode()
+
+
 def run_param_file(param_file, device=-1, write_files=True):
     """What ``./zeldovich <param_file>`` does, in-process.  Returns the run report."""
     rep = RunReport()

@@ -377,12 +377,48 @@ extern "C" int zplt_write_outputs(zplt_ctx *ctx, const char *output_dir, int32_t
     return write_ic_files(ctx, zplt_ctx_ppd_(ctx), zplt_ctx_icformat_(ctx), output_dir, cpd, qoneslab, nullptr, qdensity, density_path);
 }
 
-// density file name: ZD_density_filename with "{:d}" replaced by ppd (reference src/output.cpp:283, default "density{:d}")
+// density file name: the reference passes ZD_density_filename through fmt::format with ppd as the only argument
+// (reference src/output.cpp:283, default "density{:d}").  The subset of that mini-language a file name can sensibly use:
+// "{}", "{0}", "{:d}", "{0:d}" and zero-padded widths such as "{:05d}" become ppd; "{{" and "}}" are literal braces.
+std::string zplt_format_density_name(const std::string &pattern, long long ppd) {
+    std::string out;
+    for (size_t i = 0; i < pattern.size(); i++) {
+        const char ch = pattern[i];
+        if (ch == '{' && i + 1 < pattern.size() && pattern[i + 1] == '{') {
+            out += '{', i++;
+        } else if (ch == '}' && i + 1 < pattern.size() && pattern[i + 1] == '}') {
+            out += '}', i++;
+        } else if (ch == '{') {
+            const size_t close = pattern.find('}', i);
+            if (close == std::string::npos) {
+                out += pattern.substr(i);
+                break;
+            }
+            std::string spec = pattern.substr(i + 1, close - i - 1);  // [index][:[0][width][d]]
+            const size_t colon = spec.find(':');
+            spec               = colon == std::string::npos ? "" : spec.substr(colon + 1);
+            bool zero = !spec.empty() && spec[0] == '0';
+            size_t width = 0;
+            for (char c : spec)
+                if (c >= '0' && c <= '9') width = width * 10 + (size_t) (c - '0');
+            std::string num = std::to_string(ppd);
+            if (num.size() < width) num = std::string(width - num.size(), zero ? '0' : ' ') + num;
+            out += num;
+            i = close;
+        } else {
+            out += ch;
+        }
+    }
+    return out;
+}
+extern "C" int zplt_format_density_name_(const char *pattern, long long ppd, char *out, size_t cap) {  // test hook
+    const std::string r = zplt_format_density_name(pattern ? pattern : "", ppd);
+    if (!out || cap == 0) return (int) r.size();
+    snprintf(out, cap, "%s", r.c_str());
+    return (int) r.size();
+}
 static std::string density_path_of(const zplt_params &P) {
-    std::string name = P.density_filename;
-    const size_t pos = name.find("{:d}");
-    if (pos != std::string::npos) name.replace(pos, 4, std::to_string((long long) P.ppd));
-    return (fs::path(P.output_dir) / name).string();
+    return (fs::path(P.output_dir) / zplt_format_density_name(P.density_filename, (long long) P.ppd)).string();
 }
 
 // ---------------------------------------------------------------- whole run -------

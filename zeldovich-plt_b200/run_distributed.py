@@ -116,7 +116,7 @@ def main():
         dist.barrier()
     if qdensity:
         # one density file, planes in ascending z: rank 0 creates it ("wb", reference src/output.cpp:282-288), the others append in turn
-        name = P.density_filename.replace("{:d}", str(N))
+        name = pkg.format_density_name(P.density_filename, N)  # the reference's fmt::format(name, ppd), src/output.cpp:283
         dpath = os.path.join(outdir, name)
         for turn in range(world):
             if rank == turn:
