@@ -626,12 +626,14 @@ def main_b200(args, rank, world, local_rank):
     # ---- BASELINE configs[4]: PPD=2048 qPLT + rescale across 8 GPUs ---------------------------
     want2048 = world == 8 and args.exchange == "p2p" and not args.no_ppd2048 and N != 2048
     if want2048:
-        # every rank must be able to hold its 137 GB of slabs, or none starts (a rank failing alone would leave the others waiting)
-        ok = torch.tensor([1.0 if torch.cuda.mem_get_info(dev)[0] > (150 << 30) else 0.0], dtype=torch.float64, device=dev)
+        # every rank must be able to hold its 128 GiB of slabs plus a few record planes, or none starts (a rank failing alone
+        # would leave the others waiting in the exchange set-up)
+        torch.cuda.empty_cache()
+        ok = torch.tensor([1.0 if torch.cuda.mem_get_info(dev)[0] > (140 << 30) else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() == 0.0:
             want2048 = False
-            ppd2048 = {"error": "not every GPU has 150 GB free for the PPD=2048 slabs"}
+            ppd2048 = {"error": "not every GPU has 140 GiB free for the PPD=2048 slabs"}
     if want2048:
         try:
             pb2 = Problem(pkg, synth, zd, torch, dist, args, 2048, True, rank, world, local_rank, dev, tmp)
