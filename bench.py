@@ -615,7 +615,7 @@ def main_b200(args, rank, world, local_rank):
                 wall = time.perf_counter() - t0
                 e2e_files = {"value": N**3 / wall, "unit": UNIT, "seconds": wall, "seconds_preamble": rep.seconds_preamble,
                              "seconds_device_and_d2h": rep.seconds_device, "seconds_fwrite": rep.seconds_write,
-                             "bytes_written": int(rep.bytes_written), "files": int(rep.files_written),
+                             "bytes_written": int(rep.bytes_written), "files": int(rep.files_written), "out_of_core_passes": int(rep.ooc_passes),
                              "note": "zplt_run_param_file = what bin/zeldovich <param_file> runs: parameter file, P(k) normalisation, "
                                      f"eigenmode file, generation, every ic_* file written under {tmp} (the reference arm's e2e writes its "
                                      "files the same way)"}

@@ -137,6 +137,16 @@ int zplt_fetch_planes(zplt_ctx *ctx, int64_t z0, int64_t nz, void *host_out);
  * LOCAL index (global z = rank*ppd/nranks + local); particle ids carry the global index. */
 int zplt_exchange_info(zplt_ctx *ctx, void **send, void **recv, size_t *bytes_per_peer);
 int zplt_exchange_done(zplt_ctx *ctx);
+/* ---- out of core: one context, the ranks of a slab decomposition one after the other -------
+ * The reference built with -DDISK keeps the cube as numblock^2 block files [yblock][zblock] and passes over it twice
+ * (reference src/block_array.cpp:129-382, README "Out-of-core").  Here block (s, d) — the rows slab rank s owns, on the
+ * planes rank d owns — is exactly block d of rank s's send buffer.  zplt_slab_set_rank() makes the context rank `rank` of
+ * cfg.nranks from now on (any order, any number of times); the caller copies the send blocks out after zplt_generate()
+ * (stage 1 of rank s) and, for stage 2 of rank d, puts blocks (0..nranks-1, d) into `recv` in source order and calls
+ * zplt_exchange_adopt() instead of zplt_exchange_done().  HBM holds 2/nranks of the cube at any time.  Not with peers
+ * mapped, not with ZD_f_NL.  zplt_run_param_file() does all of this by itself when the cube does not fit the device. */
+int zplt_slab_set_rank(zplt_ctx *ctx, int32_t rank);
+int zplt_exchange_adopt(zplt_ctx *ctx);
 /* Fused exchange over NVLink peer memory (one process per GPU on one node).  Every rank exports a
  * 64-byte CUDA IPC handle of its library-owned workspace (zplt_ipc_export; do not call
  * zplt_set_workspace), the caller gathers the handles in rank order (e.g. torch.distributed
@@ -287,7 +297,15 @@ typedef struct zplt_run_report {
     double seconds_total, seconds_preamble, seconds_device, seconds_write;
     double stage_ms[4];
     int64_t ppd, files_written, bytes_written;
+    /* out-of-core runs: passes over the cube (0 = the cube was resident), 1 if the blocks went through files under
+     * InitialConditionsDirectory instead of host memory, bytes parked, seconds spent copying/writing/reading them */
+    int64_t ooc_passes, ooc_disk, ooc_bytes;
+    double seconds_blocks;
 } zplt_run_report;
+/* The cube is kept in HBM when it fits.  Otherwise — or when the environment variable ZPLT_OOC_PASSES=G forces it — the run
+ * goes out of core in G passes (see zplt_slab_set_rank), the blocks parked in host memory, or in files
+ * `zeldovich.{s}/zeldovich.{s}.{d}` under InitialConditionsDirectory (the reference's names, src/block_array.cpp:136) when
+ * host memory is too small or ZPLT_OOC_STORE=disk. */
 int zplt_run_param_file(const char *param_file, int32_t device, int32_t write_files, zplt_run_report *report);
 
 #ifdef __cplusplus

@@ -37,8 +37,8 @@ def ctx_from(pkg, P, power, rank=0, nranks=1):
     return ctx
 
 
-def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
-    """Product context from keyword parameters; the spline comes from the product's own host code."""
+def write_case_files(kw, pk, eig, **extra):
+    """Parameter file (+ P(k) table, eigenmode file) of a keyword case in a fresh directory; returns the file's path."""
     synth = load_synth()
     tmp = tempfile.mkdtemp(prefix="zplt_")
     synth.write_power_table(os.path.join(tmp, "pk.pow"), pk[0], pk[1])
@@ -64,8 +64,13 @@ def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
             f.write(np.int32(eig[0]).tobytes())
             f.write(np.ascontiguousarray(eig[1], dtype=np.float64).tobytes())
         over["ZD_PLT_filename"] = '"%s"' % synth_path
-    synth.write_param(os.path.join(tmp, "c.par"), **over)
-    P = pkg.Parameters(os.path.join(tmp, "c.par"))
+    over.update(extra)
+    return synth.write_param(os.path.join(tmp, "c.par"), **over)
+
+
+def make_ctx(pkg, kw, pk, eig, rank=0, nranks=1):
+    """Product context from keyword parameters; the spline comes from the product's own host code."""
+    P = pkg.Parameters(write_case_files(kw, pk, eig))
     power = pkg.PowerSpectrum(P)
     cfg = P.config(device=0)
     cfg.rank, cfg.nranks = rank, nranks
@@ -544,6 +549,44 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     compare_records(oracle, got, want)
     assert abs(var / wst["density_variance"] - 1) < 1e-10
     assert np.allclose(md, wst["max_disp"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("passes,store,case", [
+    (4, "ram", dict(ppd=64, icformat="RVZel")),
+    (2, "disk", dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16)),
+    (8, "ram", dict(ppd=128, qPLT=1, icformat="RVZel", eig=128)),
+    (16, "disk", dict(ppd=256, k_cutoff=2.0, icformat="Zeldovich")),
+])
+def test_out_of_core_run_matches_oracle(pkg, oracle, monkeypatch, passes, store, case):
+    """zplt_run_param_file out of core (the reference's -DDISK mode, src/block_array.cpp:129-382): one context plays the slab
+    ranks one after the other (zplt_slab_set_rank / zplt_exchange_adopt), the blocks wait in host memory or in files; HBM
+    holds 2/passes of the cube.  The ic files must hold the oracle's records."""
+    case = dict(case)
+    eig_ppd = case.pop("eig", None)
+    kw = default_kw(**case)
+    synth = load_synth()
+    eig = (eig_ppd, synth.make_eigmodes(eig_ppd)) if eig_ppd else None
+    N, cpd = kw["ppd"], 5
+    out = tempfile.mkdtemp(prefix="zplt_ooc_")
+    par = write_case_files(kw, helpers.wmap_pk(), eig, InitialConditionsDirectory='"%s"' % out, CPD=cpd)
+    monkeypatch.setenv("ZPLT_OOC_PASSES", str(passes))
+    monkeypatch.setenv("ZPLT_OOC_STORE", store)
+    rep = pkg.run_param_file(par, device=0)
+    assert rep.ooc_passes == passes and rep.ooc_disk == (store == "disk")
+    assert rep.ooc_bytes == 16 * (4 if kw["qPLT"] else 2) * N**3
+    got = oracle.read_ic_dir(out, N, cpd, kw["icformat"])
+    want, wst = oracle.run(oracle.make_config(**kw), helpers.wmap_pk(), eig)
+    compare_records(oracle, got, want)
+    assert abs(rep.density_variance / wst["density_variance"] - 1) < 1e-10
+    assert np.allclose(np.array(rep.max_disp[:]), wst["max_disp"], rtol=1e-10)
+    assert sorted(os.listdir(out)) == sorted({"ic_%d" % (z * cpd // N) for z in range(N)})  # no block files left behind
+    # the same parameter file with the cube resident gives the same bytes
+    monkeypatch.setenv("ZPLT_OOC_PASSES", "0")
+    rep1 = pkg.run_param_file(par, device=0)
+    assert rep1.ooc_passes == 0
+    again = oracle.read_ic_dir(out, N, cpd, kw["icformat"])
+    compare_records(oracle, again, want)
+    print("out-of-core records byte-identical to the resident run:", np.array_equal(again.view(np.uint8), got.view(np.uint8)))
 
 
 @pytest.mark.parametrize("G,opts,case", [

@@ -240,3 +240,120 @@ def test_bench_line_helpers():
     ppd, why = bench.ref_ppd_for(args, True)
     assert ppd in (128, 256, 512, 1024) and why
     assert bench.ref_ppd_for(argparse.Namespace(ref_ppd=256, ppd=1024), True)[0] == 256
+
+
+# ------------------------------------------------------------------ out-of-core scheduling ----
+@pytest.fixture(scope="module")
+def mocklib():
+    """The UNMODIFIED host half (host/*.cpp) linked against tests/mock_device.cpp instead of the CUDA half: the pass
+    scheduling, the block store and the ic file writer of zplt_run_param_file run on this machine, no GPU involved."""
+    import ctypes as C
+    import subprocess
+
+    pkg = load_package()
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libzplt_mockdev.so")
+    host = os.path.join(ROOT, "zeldovich-plt_b200", "host")
+    srcs = [os.path.join(host, f) for f in ("ParseHeader.cpp", "host_parameters.cpp", "host_power.cpp", "host_api.cpp")]
+    srcs.append(os.path.join(ROOT, "tests", "mock_device.cpp"))
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-std=gnu++17", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", *srcs, "-o", so])
+    L = C.CDLL(so)
+    L.zplt_run_param_file.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(pkg.RunReport)]
+    L.zplt_last_error.restype = C.c_char_p
+    return L, pkg
+
+
+def _mock_run(mocklib, tmp, env, write_files=1, **over):
+    import ctypes as C
+
+    L, pkg = mocklib
+    out = os.path.join(tmp, "ic")
+    par = write_case(tmp, InitialConditionsDirectory='"%s"' % out, **over)
+    rep = pkg.RunReport()
+    keys = ("ZPLT_OOC_PASSES", "ZPLT_OOC_STORE", "ZPLT_MOCK_FREE_BYTES")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    os.environ.update(env)
+    try:
+        rc = L.zplt_run_param_file(os.fsencode(par), 0, write_files, C.byref(rep))
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    return rc, rep, out, L.zplt_last_error().decode()
+
+
+def _check_mock_files(out, ppd, cpd, rb, planes=None):
+    """Every ic file holds exactly its planes (z*cpd/ppd == file number) in ascending z, each with the mock's pattern."""
+    planes = list(range(ppd)) if planes is None else planes
+    words = ppd * ppd * rb // 4
+    j = np.arange(words, dtype=np.uint32) & 0xFFFFF
+    want = {}
+    for z in planes:
+        want.setdefault(z * cpd // ppd, []).append(z)
+    got = sorted(f for f in os.listdir(out) if f.startswith("ic_"))
+    assert got == sorted(f"ic_{k}" for k in want), got
+    for k, zs in want.items():
+        data = np.fromfile(os.path.join(out, f"ic_{k}"), dtype=np.uint32)
+        assert data.size == len(zs) * words, (k, data.size)
+        for i, z in enumerate(zs):
+            assert np.array_equal(data[i * words:(i + 1) * words], (np.uint32(z) << np.uint32(20)) ^ j), (k, z)
+
+
+@pytest.mark.parametrize("store", ["ram", "disk"])
+@pytest.mark.parametrize("passes,ppd,cpd,fmt,qplt", [(4, 32, 5, "RVZel", 0), (2, 16, 16, "RVdoubleZel", 1), (8, 32, 3, "ZelSimple", 0), (16, 32, 32, "Zeldovich", 0)])
+def test_out_of_core_pass_scheduling(mocklib, store, passes, ppd, cpd, fmt, qplt):
+    """zplt_run_param_file out of core (reference -DDISK, src/block_array.cpp:129-382): block (s, d) must reach rank d's receive
+    buffer at position s (the mock's zplt_exchange_adopt checks every value), planes must reach the ic files in ascending z,
+    block files carry the reference's names while they exist and are gone afterwards."""
+    synth = load_synth()
+    with tempfile.TemporaryDirectory() as tmp:
+        over = dict(NP=ppd**3, CPD=cpd, ICFormat='"%s"' % fmt)
+        if qplt:
+            synth.write_eigmodes(os.path.join(tmp, "eig"), 8)
+            over.update(ZD_qPLT=1, ZD_PLT_filename='"%s"' % os.path.join(tmp, "eig"))
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": str(passes), "ZPLT_OOC_STORE": store}, **over)
+        assert rc == 0, err
+        rb = {"RVZel": 32, "RVdoubleZel": 56, "ZelSimple": 12, "Zeldovich": 32}[fmt]
+        _check_mock_files(out, ppd, cpd, rb)
+        assert rep.ooc_passes == passes and rep.ooc_disk == (store == "disk")
+        assert rep.ooc_bytes == 16 * (4 if qplt else 2) * ppd**3  # the whole cube went out once
+        assert rep.density_variance == ppd  # (mock) planes that went through the emission: each exactly once
+        assert rep.max_disp[0] == passes  # (mock) one generation per pass
+        assert rep.bytes_written == ppd**3 * rb and rep.files_written == len({z * cpd // ppd for z in range(ppd)})
+        assert not [f for f in os.listdir(out) if f.startswith("zeldovich.")]  # block directories removed
+
+
+def test_out_of_core_options_and_auto_passes(mocklib):
+    ppd = 32
+    cube = 16 * 2 * ppd**3
+    with tempfile.TemporaryDirectory() as tmp:
+        # the cube fits: resident run, no passes
+        rc, rep, out, err = _mock_run(mocklib, tmp, {}, NP=ppd**3, CPD=4)
+        assert rc == 0 and rep.ooc_passes == 0, err
+        _check_mock_files(out, ppd, 4, 32)
+    with tempfile.TemporaryDirectory() as tmp:
+        # free HBM for a quarter of the cube twice over (+ the fixed 1 GiB allowance and the padding room): 8 passes, not 4
+        free = (1 << 30) + 2 * cube // 8 + (ppd // 8) * 8192 * 16
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_MOCK_FREE_BYTES": str(free)}, NP=ppd**3, CPD=4, ZD_qdensity=1,
+                                      ZD_density_filename='"dens{:d}"')
+        assert rc == 0 and rep.ooc_passes == 8 and rep.ooc_disk == 0, (err, rep.ooc_passes)
+        _check_mock_files(out, ppd, 4, 32)
+        dens = np.fromfile(os.path.join(out, f"dens{ppd}"), dtype=np.float32).reshape(ppd, ppd * ppd)
+        assert np.array_equal(dens, np.repeat(np.arange(ppd, dtype=np.float32)[:, None], ppd * ppd, axis=1))
+    with tempfile.TemporaryDirectory() as tmp:
+        # ZD_qoneslab: one plane, from the pass that owns it; statistics-only runs (write_files = 0) still emit every plane
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": "4"}, NP=ppd**3, CPD=4, ZD_qoneslab=21)
+        assert rc == 0, err
+        _check_mock_files(out, ppd, 4, 32, planes=[21])
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": "4", "ZPLT_OOC_STORE": "disk"}, write_files=0, NP=ppd**3, CPD=4)
+        assert rc == 0 and rep.density_variance == ppd and rep.files_written == 0, err
+    with tempfile.TemporaryDirectory() as tmp:
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": "3"}, NP=ppd**3, CPD=4)
+        assert rc != 0 and "ZPLT_OOC_PASSES" in err
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_MOCK_FREE_BYTES": str(1 << 20)}, NP=ppd**3, CPD=4)
+        assert rc != 0 and "16 passes" in err
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": "2", "ZPLT_OOC_STORE": "tape"}, NP=ppd**3, CPD=4)
+        assert rc != 0 and "ZPLT_OOC_STORE" in err

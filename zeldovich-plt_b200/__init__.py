@@ -84,6 +84,7 @@ class RunReport(C.Structure):
         ("seconds_total", C.c_double), ("seconds_preamble", C.c_double), ("seconds_device", C.c_double),
         ("seconds_write", C.c_double), ("stage_ms", C.c_double * 4),
         ("ppd", C.c_int64), ("files_written", C.c_int64), ("bytes_written", C.c_int64),
+        ("ooc_passes", C.c_int64), ("ooc_disk", C.c_int64), ("ooc_bytes", C.c_int64), ("seconds_blocks", C.c_double),
     ]
 
 
@@ -94,7 +95,7 @@ EXPORTS = [
     "zplt_generate", "zplt_emit_planes", "zplt_fetch_planes", "zplt_emit_planes_density", "zplt_fetch_planes_density",
     "zplt_write_outputs", "zplt_reset_stats", "zplt_get_stats", "zplt_synchronize",
     "zplt_get_timings", "zplt_set_option", "zplt_dbg_set_peers", "zplt_dbg_spectral_hot", "zplt_dbg_hot_draws", "zplt_dbg_fft_variant",
-    "zplt_exchange_info", "zplt_exchange_done", "zplt_ipc_export", "zplt_ipc_import", "zplt_ipc_close", "zplt_potential_begin", "zplt_potential_exchange", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
+    "zplt_exchange_info", "zplt_exchange_done", "zplt_slab_set_rank", "zplt_exchange_adopt", "zplt_ipc_export", "zplt_ipc_import", "zplt_ipc_close", "zplt_potential_begin", "zplt_potential_exchange", "zplt_slab_owner", "zplt_slab_offset", "zplt_dbg_pcg_draws", "zplt_dbg_mode_draws", "zplt_dbg_power_table", "zplt_dbg_spectral",
     "zplt_dbg_after_generate", "zplt_dbg_fft", "zplt_params_load", "zplt_icformat_code", "zplt_config_from_params",
     "zplt_power_create", "zplt_power_destroy", "zplt_power_info", "zplt_power_arrays", "zplt_power_eval",
     "zplt_power_sigmaR", "zplt_power_infer_Tk", "zplt_power_primordial_norm", "zplt_power_apply", "zplt_load_eigenmodes_file", "zplt_write_ic_files", "zplt_run_param_file",
@@ -139,6 +140,8 @@ def lib():
     L.zplt_get_timings.argtypes = [vp, dp]
     L.zplt_exchange_info.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.zplt_exchange_done.argtypes = [vp]
+    L.zplt_slab_set_rank.argtypes = [vp, i32]
+    L.zplt_exchange_adopt.argtypes = [vp]
     L.zplt_ipc_export.argtypes = [vp, C.c_char_p]
     L.zplt_ipc_import.argtypes = [vp, i32, C.c_char_p]
     L.zplt_ipc_close.argtypes = [vp]
@@ -388,6 +391,15 @@ class Context:
 
     def exchange_done(self):
         _ck(lib().zplt_exchange_done(self._h))
+
+    def slab_set_rank(self, rank):
+        """Out of core: this context is slab rank ``rank`` from now on (zplt_slab_set_rank)."""
+        _ck(lib().zplt_slab_set_rank(self._h, rank))
+        self.cfg.rank = rank
+
+    def exchange_adopt(self):
+        """Out of core: the caller has filled the receive buffer with this rank's blocks (zplt_exchange_adopt)."""
+        _ck(lib().zplt_exchange_adopt(self._h))
 
     def reset_stats(self):
         _ck(lib().zplt_reset_stats(self._h))

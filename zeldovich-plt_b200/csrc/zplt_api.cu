@@ -1022,6 +1022,37 @@ extern "C" int zplt_exchange_done(zplt_ctx *c) {
     return ZPLT_OK;
 }
 
+// Out-of-core runs: ONE context plays the ranks of a slab decomposition one after the other, the blocks of the exchange parked
+// in host memory or files by the caller in between (host/host_api.cpp, run_out_of_core; reference -DDISK BlockArray,
+// src/block_array.cpp:129-382).  Nothing the context holds besides SlabGeom::rank depends on the rank: the generator tables are
+// per y-plane of the whole grid, the layout math takes the rank as an argument.
+extern "C" int zplt_slab_set_rank(zplt_ctx *c, int32_t rank) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (c->sg.G == 1) return fail(ZPLT_EINVAL, "a single-GPU context has no slab ranks");
+    if (rank < 0 || rank >= c->sg.G) return fail(ZPLT_EINVAL, "bad rank %d of %d", rank, c->sg.G);
+    if (c->p2p) return fail(ZPLT_ESTATE, "peers are mapped: this context is one fixed rank of a running job");
+    if (c->cfg.f_NL != 0.) return fail(ZPLT_EINVAL, "ZD_f_NL: the potential pass is staged per rank, a context cannot change rank");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));  // nothing of the previous rank is still in flight
+    c->sg.rank = c->cfg.rank = rank;
+    c->generated = c->exchanged = false;
+    return ZPLT_OK;
+}
+
+// The caller has put this rank's blocks B2[src][zl][a][slot][x] into the receive buffer itself (zplt_exchange_info says where),
+// without zplt_generate having run for this rank in this context: emission may start.
+extern "C" int zplt_exchange_adopt(zplt_ctx *c) {
+    if (!c) return fail(ZPLT_EINVAL, "null context");
+    if (c->sg.G == 1) return fail(ZPLT_EINVAL, "a single-GPU context has no exchange");
+    if (c->p2p) return fail(ZPLT_ESTATE, "the exchange is fused into zplt_generate (peers are mapped)");
+    if (!c->cube) return fail(ZPLT_ESTATE, "no workspace yet (zplt_exchange_info allocates it)");
+    int rc = ready(c);
+    if (rc) return rc;
+    c->n_emit_ev = 0;
+    c->generated = c->exchanged = true;
+    return ZPLT_OK;
+}
+
 extern "C" int zplt_slab_owner(int64_t ppd, int32_t nranks, int64_t y, int32_t *rank, int32_t *slot) {
     if (nranks < 1 || ppd < 2 || (ppd / 2) % nranks || y < 0 || y >= ppd || !rank || !slot) return fail(ZPLT_EINVAL, "bad arguments");
     int r, s;
@@ -1258,4 +1289,19 @@ extern "C" void *zplt_pinned_alloc_(size_t bytes) {
 }
 extern "C" void zplt_pinned_free_(void *p) {
     if (p) cudaFreeHost(p);
+}
+// plain copies between the workspace and host memory, and the free HBM of a device (out-of-core driver, host/host_api.cpp)
+extern "C" int zplt_copy_d2h_(void *host, const void *dev, size_t bytes) {
+    CK(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+    return ZPLT_OK;
+}
+extern "C" int zplt_copy_h2d_(void *dev, const void *host, size_t bytes) {
+    CK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+    return ZPLT_OK;
+}
+extern "C" int zplt_device_free_bytes_(int device, size_t *free_b) {
+    size_t total = 0;
+    if (device >= 0) CK(cudaSetDevice(device));
+    CK(cudaMemGetInfo(free_b, &total));
+    return ZPLT_OK;
 }

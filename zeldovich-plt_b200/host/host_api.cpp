@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -269,96 +270,130 @@ static bool run_write_jobs(const fs::path &dir, const std::vector<WriteJob> &job
 // The planes come off the device in chunks into two pinned staging buffers: while the writer threads append chunk i to its
 // ic files, the device emits and copies chunk i+1.  Append order per file stays ascending z: a file's planes inside a chunk
 // are one job, and a chunk is finished before the next one is handed to the writers.
-static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, int qoneslab, WriteStats *ws,
-                          int qdensity = 0, const char *density_path = nullptr) {
-    fs::path dir(output_dir);
-    std::error_code ec;
-    if (fs::exists(dir, ec)) {
-        for (const auto &entry : fs::directory_iterator(dir, ec)) {
-            if (!entry.is_regular_file()) continue;
-            const std::string fn = entry.path().filename().string();
-            if (fn.compare(0, 3, "ic_") == 0 || fn.compare(0, 10, "zeldovich.") == 0) fs::remove(entry.path(), ec);
-        }
-    }
-    fs::create_directories(dir, ec);
-    if (ec) return hfail(ZPLT_EINVAL, "cannot create output directory \"%s\"", output_dir);
+// open() once, then write() for consecutive ranges of global planes in ascending order — the whole grid from a context that
+// holds it, or one slab rank's planes at a time (out-of-core runs).
+struct IcWriter {
+    fs::path dir;
+    int64_t ppd = 0, chunk = 1, zbeg = 0, zend = 0, last_file = -1;
+    int cpd = 1, qdensity = 0, nthreads = 1;
+    size_t plane = 0, dplane = 0;
+    bool records = true, two = false;
+    std::unique_ptr<HostBuffer> buf[2], dbuf[2];
+    FILE *densfp   = nullptr;
+    WriteStats *ws = nullptr;
 
-    const size_t rb    = zplt_record_bytes(icformat);
-    const size_t plane = (size_t) ppd * ppd * rb;
-    int64_t chunk      = (int64_t) ((1024ull << 20) / plane);
-    if (chunk < 1) chunk = 1;
-    if (chunk > ppd) chunk = ppd;
-    const bool records = qdensity != 2;
-    int64_t zbeg = 0, zend = ppd;
-    if (qoneslab >= 0) {
-        if (qoneslab >= ppd) return ZPLT_OK;  // the reference's loop simply never matches
-        zbeg = qoneslab, zend = qoneslab + 1;
+    ~IcWriter() { close(); }
+    void close() {
+        if (densfp) fclose(densfp);
+        densfp = nullptr;
     }
-    const bool two = zend - zbeg > chunk;  // a second staging buffer only when there is a second chunk to overlap with
-    HostBuffer buf0(records ? (size_t) chunk * plane : 16), buf1(records && two ? (size_t) chunk * plane : 16);
-    if (!buf0.p || !buf1.p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host staging", (size_t) chunk * plane);
-    // ZD_qdensity: float32 density planes appended to one file, opened "wb" (reference src/output.cpp:282-288)
-    const size_t dplane = (size_t) ppd * ppd * sizeof(float);
-    HostBuffer dbuf0(qdensity ? (size_t) chunk * dplane : 16), dbuf1(qdensity && two ? (size_t) chunk * dplane : 16);
-    if (!dbuf0.p || !dbuf1.p) return hfail(ZPLT_ENOMEM, "cannot allocate host staging for the density planes");
-    FILE *densfp = nullptr;
-    if (qdensity) {
-        if (!density_path) return hfail(ZPLT_EINVAL, "ZD_qdensity needs a density file name");
-        densfp = fopen(density_path, "wb");
-        if (!densfp) return hfail(ZPLT_EINVAL, "cannot open density file \"%s\"", density_path);
-    }
-    unsigned char *rbuf[2] = {buf0.p, two ? buf1.p : buf0.p};
-    unsigned char *dbuf[2] = {dbuf0.p, two ? dbuf1.p : dbuf0.p};
-    int nthreads = (int) std::thread::hardware_concurrency();
-    if (nthreads > 8) nthreads = 8;
-    if (nthreads < 1) nthreads = 1;
 
-    auto fetch = [&](int64_t z0, int which) -> int {
-        const int64_t nz = (z0 + chunk <= zend) ? chunk : zend - z0;
-        return zplt_fetch_planes_density(ctx, z0, nz, records ? rbuf[which] : nullptr, qdensity ? (float *) dbuf[which] : nullptr);
-    };
-    int rc = fetch(zbeg, 0);
-    int64_t last_file = -1;
-    int which         = 0;
-    for (int64_t z0 = zbeg; rc == ZPLT_OK && z0 < zend; z0 += chunk, which ^= 1) {
-        const int64_t nz = (z0 + chunk <= zend) ? chunk : zend - z0;
-        // what the writers do with this chunk
-        std::vector<WriteJob> jobs;
-        for (int64_t z = z0; records && z < z0 + nz; z++) {
-            const int64_t fileno = z * cpd / ppd;  // integer division, reference src/output.cpp:208
-            if (!jobs.empty() && jobs.back().fileno == fileno) {
-                jobs.back().bytes += plane;
-            } else {
-                jobs.push_back({fileno, rbuf[which] + (size_t) (z - z0) * plane, plane});
-                if (fileno != last_file && ws) ws->files++;
-                last_file = fileno;
+    int open(int64_t ppd_, int icformat, const char *output_dir, int cpd_, int qoneslab, WriteStats *ws_, int qdensity_, const char *density_path) {
+        ppd = ppd_, cpd = cpd_, ws = ws_, qdensity = qdensity_;
+        dir = fs::path(output_dir);
+        std::error_code ec;
+        if (fs::exists(dir, ec)) {
+            for (const auto &entry : fs::directory_iterator(dir, ec)) {
+                if (!entry.is_regular_file()) continue;
+                const std::string fn = entry.path().filename().string();
+                if (fn.compare(0, 3, "ic_") == 0 || fn.compare(0, 10, "zeldovich.") == 0) fs::remove(entry.path(), ec);
             }
         }
-        const double t0 = now_s();
-        std::string werr;
-        bool wok = true;
-        int rc_next = ZPLT_OK;
-        {
-            // the writers work on this chunk while this thread drives the device through the next one
-            std::thread writers([&]() {
-                if (densfp && fwrite(dbuf[which], 1, (size_t) nz * dplane, densfp) != (size_t) nz * dplane) {
-                    wok  = false;
-                    werr = "short write on the density file";
-                    return;
-                }
-                wok = run_write_jobs(dir, jobs, nthreads, &werr);
-            });
-            if (z0 + chunk < zend) rc_next = fetch(z0 + chunk, which ^ 1);
-            writers.join();
+        fs::create_directories(dir, ec);
+        if (ec) return hfail(ZPLT_EINVAL, "cannot create output directory \"%s\"", output_dir);
+
+        plane  = (size_t) ppd * ppd * zplt_record_bytes(icformat);
+        dplane = (size_t) ppd * ppd * sizeof(float);
+        chunk  = (int64_t) ((1024ull << 20) / plane);
+        if (chunk < 1) chunk = 1;
+        if (chunk > ppd) chunk = ppd;
+        records = qdensity != 2;
+        zbeg = 0, zend = ppd;
+        if (qoneslab >= 0) {
+            zbeg = qoneslab, zend = qoneslab + 1;
+            if (qoneslab >= ppd) zbeg = zend = 0;  // the reference's loop simply never matches
         }
-        if (ws) {
-            ws->seconds += now_s() - t0;
-            ws->bytes += (int64_t) ((records ? (size_t) nz * plane : 0) + (densfp ? (size_t) nz * dplane : 0));
+        two = zend - zbeg > chunk;  // a second staging buffer only when there is a second chunk to overlap with
+        buf[0].reset(new HostBuffer(records ? (size_t) chunk * plane : 16));
+        buf[1].reset(new HostBuffer(records && two ? (size_t) chunk * plane : 16));
+        if (!buf[0]->p || !buf[1]->p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host staging", (size_t) chunk * plane);
+        // ZD_qdensity: float32 density planes appended to one file, opened "wb" (reference src/output.cpp:282-288)
+        dbuf[0].reset(new HostBuffer(qdensity ? (size_t) chunk * dplane : 16));
+        dbuf[1].reset(new HostBuffer(qdensity && two ? (size_t) chunk * dplane : 16));
+        if (!dbuf[0]->p || !dbuf[1]->p) return hfail(ZPLT_ENOMEM, "cannot allocate host staging for the density planes");
+        if (qdensity) {
+            if (!density_path) return hfail(ZPLT_EINVAL, "ZD_qdensity needs a density file name");
+            densfp = fopen(density_path, "wb");
+            if (!densfp) return hfail(ZPLT_EINVAL, "cannot open density file \"%s\"", density_path);
         }
-        if (!wok) rc = hfail(ZPLT_EINVAL, "%s", werr.c_str());
-        else rc = rc_next;
+        nthreads = (int) std::thread::hardware_concurrency();
+        if (nthreads > 8) nthreads = 8;
+        if (nthreads < 1) nthreads = 1;
+        return ZPLT_OK;
     }
-    if (densfp) fclose(densfp);
+
+    // the context's planes [0, nplanes) are the global planes [zglobal0, zglobal0 + nplanes)
+    int write(zplt_ctx *ctx, int64_t zglobal0, int64_t nplanes) {
+        const int64_t a = std::max(zbeg, zglobal0), b = std::min(zend, zglobal0 + nplanes);
+        if (a >= b) return ZPLT_OK;
+        unsigned char *rbuf[2] = {buf[0]->p, two ? buf[1]->p : buf[0]->p};
+        unsigned char *dbf[2]  = {dbuf[0]->p, two ? dbuf[1]->p : dbuf[0]->p};
+        auto fetch = [&](int64_t z0, int which) -> int {
+            const int64_t nz = (z0 + chunk <= b) ? chunk : b - z0;
+            return zplt_fetch_planes_density(ctx, z0 - zglobal0, nz, records ? rbuf[which] : nullptr, qdensity ? (float *) dbf[which] : nullptr);
+        };
+        int rc    = fetch(a, 0);
+        int which = 0;
+        for (int64_t z0 = a; rc == ZPLT_OK && z0 < b; z0 += chunk, which ^= 1) {
+            const int64_t nz = (z0 + chunk <= b) ? chunk : b - z0;
+            // what the writers do with this chunk
+            std::vector<WriteJob> jobs;
+            for (int64_t z = z0; records && z < z0 + nz; z++) {
+                const int64_t fileno = z * cpd / ppd;  // integer division, reference src/output.cpp:208
+                if (!jobs.empty() && jobs.back().fileno == fileno) {
+                    jobs.back().bytes += plane;
+                } else {
+                    jobs.push_back({fileno, rbuf[which] + (size_t) (z - z0) * plane, plane});
+                    if (fileno != last_file && ws) ws->files++;
+                    last_file = fileno;
+                }
+            }
+            const double t0 = now_s();
+            std::string werr;
+            bool wok    = true;
+            int rc_next = ZPLT_OK;
+            {
+                // the writers work on this chunk while this thread drives the device through the next one
+                std::thread writers([&]() {
+                    if (densfp && fwrite(dbf[which], 1, (size_t) nz * dplane, densfp) != (size_t) nz * dplane) {
+                        wok  = false;
+                        werr = "short write on the density file";
+                        return;
+                    }
+                    wok = run_write_jobs(dir, jobs, nthreads, &werr);
+                });
+                if (z0 + chunk < b) rc_next = fetch(z0 + chunk, which ^ 1);
+                writers.join();
+            }
+            if (ws) {
+                ws->seconds += now_s() - t0;
+                ws->bytes += (int64_t) ((records ? (size_t) nz * plane : 0) + (densfp ? (size_t) nz * dplane : 0));
+            }
+            if (!wok)
+                rc = hfail(ZPLT_EINVAL, "%s", werr.c_str());
+            else
+                rc = rc_next;
+        }
+        return rc;
+    }
+};
+
+static int write_ic_files(zplt_ctx *ctx, int64_t ppd, int icformat, const char *output_dir, int cpd, int qoneslab, WriteStats *ws,
+                          int qdensity = 0, const char *density_path = nullptr) {
+    IcWriter w;
+    int rc = w.open(ppd, icformat, output_dir, cpd, qoneslab, ws, qdensity, density_path);
+    if (rc == ZPLT_OK) rc = w.write(ctx, 0, ppd);
+    w.close();
     return rc;
 }
 
@@ -421,6 +456,217 @@ static std::string density_path_of(const zplt_params &P) {
     return (fs::path(P.output_dir) / zplt_format_density_name(P.density_filename, (long long) P.ppd)).string();
 }
 
+// ---------------------------------------------------------------- out of core ----
+// The reference compiled with -DDISK never holds the cube: ZeldovichZ leaves it as numblock^2 block files
+// TMPDIR/zeldovich.{yblock}/zeldovich.{yblock}.{zblock}, ZeldovichXY reads them back one z-block of planes at a time
+// (reference src/block_array.cpp:129-382, src/zeldovich.cpp:891-905).  The same two passes here, with the slab
+// decomposition as the blocking: block (s, d) = the rows slab rank s owns on the planes rank d owns = block d of rank s's
+// send buffer.  One context plays rank 0..G-1 twice (zplt_slab_set_rank); HBM holds 2/G of the cube.
+extern "C" int zplt_copy_d2h_(void *host, const void *dev, size_t bytes);
+extern "C" int zplt_copy_h2d_(void *dev, const void *host, size_t bytes);
+extern "C" int zplt_device_free_bytes_(int device, size_t *free_b);
+
+struct BlockStore {
+    int G      = 0;
+    size_t blk = 0;
+    bool disk  = false;
+    fs::path dir;
+    std::vector<std::unique_ptr<HostBuffer>> ram;  // [d]: blocks (0..G-1, d), released once rank d has emitted
+    std::unique_ptr<HostBuffer> bounce;             // disk: one block on its way to or from a file
+    double seconds = 0;
+    int64_t bytes  = 0;
+
+    ~BlockStore() { close(); }
+    fs::path block_dir(int s) const { return dir / ("zeldovich." + std::to_string(s)); }
+    fs::path block_file(int s, int d) const { return block_dir(s) / ("zeldovich." + std::to_string(s) + "." + std::to_string(d)); }
+
+    int open(int G_, size_t blk_, bool disk_, const fs::path &dir_) {
+        G = G_, blk = blk_, disk = disk_, dir = dir_;
+        if (disk) {
+            std::error_code ec;
+            for (int s = 0; s < G; s++) {
+                fs::create_directories(block_dir(s), ec);
+                if (ec) return hfail(ZPLT_EINVAL, "cannot create block directory \"%s\"", block_dir(s).c_str());
+            }
+            bounce.reset(new HostBuffer(blk));
+            if (!bounce->p) return hfail(ZPLT_ENOMEM, "cannot allocate a %zu-byte block buffer", blk);
+        } else {
+            ram.resize(G);
+            for (int d = 0; d < G; d++) {
+                ram[d].reset(new HostBuffer((size_t) G * blk));
+                if (!ram[d]->p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host memory for the blocks of pass %d", (size_t) G * blk, d);
+            }
+        }
+        return ZPLT_OK;
+    }
+    int put(int s, int d, const void *dev) {
+        const double t0 = now_s();
+        int rc;
+        if (!disk) {
+            rc = zplt_copy_d2h_(ram[d]->p + (size_t) s * blk, dev, blk);
+        } else if ((rc = zplt_copy_d2h_(bounce->p, dev, blk)) == ZPLT_OK) {
+            FILE *fp  = fopen(block_file(s, d).c_str(), "wb");
+            bool good = fp && fwrite(bounce->p, 1, blk, fp) == blk;
+            if (fp) good = (fclose(fp) == 0) && good;
+            if (!good) rc = hfail(ZPLT_EINVAL, "cannot write block file \"%s\"", block_file(s, d).c_str());
+        }
+        seconds += now_s() - t0;
+        bytes += (int64_t) blk;
+        return rc;
+    }
+    int get(int s, int d, void *dev) {
+        const double t0 = now_s();
+        int rc;
+        if (!disk) {
+            rc = zplt_copy_h2d_(dev, ram[d]->p + (size_t) s * blk, blk);
+        } else {
+            FILE *fp  = fopen(block_file(s, d).c_str(), "rb");
+            bool good = fp && fread(bounce->p, 1, blk, fp) == blk;
+            if (fp) fclose(fp);
+            rc = good ? zplt_copy_h2d_(dev, bounce->p, blk) : hfail(ZPLT_EINVAL, "cannot read block file \"%s\"", block_file(s, d).c_str());
+            std::error_code ec;
+            fs::remove(block_file(s, d), ec);  // the reference's quickdelete: the space goes to the ic files
+        }
+        seconds += now_s() - t0;
+        return rc;
+    }
+    void release(int d) {
+        if (!disk && d < (int) ram.size()) ram[d].reset();
+    }
+    void close() {
+        ram.clear();
+        if (disk) {
+            std::error_code ec;
+            for (int s = 0; s < G; s++) {
+                for (int d = 0; d < G; d++) fs::remove(block_file(s, d), ec);
+                fs::remove(block_dir(s), ec);
+            }
+        }
+        bounce.reset();
+        G = 0;
+    }
+};
+
+static int64_t host_mem_available() {  // bytes, 0 if unknown
+    std::ifstream f("/proc/meminfo");
+    std::string key;
+    long long kb;
+    while (f >> key >> kb) {
+        if (key == "MemAvailable:") return (int64_t) kb * 1024;
+        f.ignore(256, '\n');
+    }
+    return 0;
+}
+
+// HBM a context of `G` slab ranks needs on top of its tables: the cube (G = 1), or stage-1 + stage-2 buffer with the room for
+// padded planes (csrc/zplt_api.cu, zplt_create), plus the fetch staging and the small areas
+static size_t device_need(int64_t N, int na, int G) {
+    const size_t cube = (size_t) 16 * na * N * N * N;
+    const size_t work = G == 1 ? cube : 2 * (cube / G) + (size_t) (N / G) * 8192 * 16;
+    return work + (1ull << 30);
+}
+
+// 0 = the cube stays in HBM; otherwise the number of passes.  ZPLT_OOC_PASSES forces a value (tests, or to leave HBM to others).
+static int choose_passes(const zplt_params &P, const zplt_config &cfg, int device, int *out) {
+    const int64_t N = P.ppd;
+    const int na    = cfg.qPLT ? 4 : 2;
+    *out            = 0;
+    if (const char *e = getenv("ZPLT_OOC_PASSES")) {
+        const int G = atoi(e);
+        if (G == 0 || G == 1) return ZPLT_OK;
+        if (G < 0 || G > 16 || (N / 2) % G) return hfail(ZPLT_EINVAL, "ZPLT_OOC_PASSES=%d: the passes must divide ppd/2=%lld and be at most 16", G, (long long) (N / 2));
+        *out = G;
+        return ZPLT_OK;
+    }
+    size_t free_b = 0;
+    int rc        = zplt_device_free_bytes_(device, &free_b);
+    if (rc) return rc;
+    const size_t extra = cfg.f_NL != 0. ? (size_t) 16 * N * N * N : 0;
+    if (device_need(N, na, 1) + extra <= free_b) return ZPLT_OK;
+    if (cfg.f_NL != 0.)
+        return hfail(ZPLT_ENOMEM, "ppd=%lld with ZD_f_NL needs %.1f GB of HBM (%.1f GB free) and does not run out of core; use slab ranks on more GPUs",
+                     (long long) N, (device_need(N, na, 1) + extra) / 1e9, free_b / 1e9);
+    if (N & (N - 1)) return hfail(ZPLT_ENOMEM, "ppd=%lld needs %.1f GB of HBM (%.1f GB free); only power-of-two grids run out of core", (long long) N, device_need(N, na, 1) / 1e9, free_b / 1e9);
+    for (int G = 2; G <= 16; G *= 2) {
+        if ((N / 2) % G == 0 && device_need(N, na, G) <= free_b) {
+            *out = G;
+            return ZPLT_OK;
+        }
+    }
+    return hfail(ZPLT_ENOMEM, "ppd=%lld does not fit this device even in 16 passes (%.1f GB needed, %.1f GB free)", (long long) N,
+                 device_need(N, na, 16) / 1e9, free_b / 1e9);
+}
+
+// the emission without keeping the records (statistics only)
+static int drain_planes(zplt_ctx *ctx, int64_t ppd, int icformat, int64_t nplanes) {
+    const size_t plane = (size_t) ppd * ppd * zplt_record_bytes(icformat);
+    int64_t chunk      = (int64_t) ((512ull << 20) / plane);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nplanes) chunk = nplanes;
+    HostBuffer buf((size_t) chunk * plane);
+    if (!buf.p) return hfail(ZPLT_ENOMEM, "cannot allocate host staging");
+    for (int64_t z0 = 0; z0 < nplanes; z0 += chunk) {
+        const int64_t nz = (z0 + chunk <= nplanes) ? chunk : nplanes - z0;
+        if (int rc = zplt_fetch_planes(ctx, z0, nz, buf.p)) return rc;
+    }
+    return ZPLT_OK;
+}
+
+static int run_out_of_core(zplt_ctx *ctx, const zplt_params &P, const zplt_config &cfg, int G, int write_files, zplt_run_report *rep, WriteStats *ws) {
+    void *send = nullptr, *recv = nullptr;
+    size_t blk = 0;
+    int rc     = zplt_exchange_info(ctx, &send, &recv, &blk);
+    if (rc) return rc;
+    const int64_t cube_bytes = (int64_t) G * G * (int64_t) blk;
+    bool disk                = false;
+    if (const char *e = getenv("ZPLT_OOC_STORE")) {
+        if (strcmp(e, "disk") == 0)
+            disk = true;
+        else if (strcmp(e, "ram") != 0)
+            return hfail(ZPLT_EINVAL, "ZPLT_OOC_STORE must be \"ram\" or \"disk\"");
+    } else {
+        const int64_t avail = host_mem_available();
+        disk                = avail > 0 && cube_bytes + (cube_bytes >> 4) + (8ll << 30) > avail;
+    }
+    fprintf(stderr, "Out of core: %d passes over %.3f GiB, blocks of %.3f GiB buffered %s\n", G, cube_bytes / 1073741824.0,
+            blk / 1073741824.0, disk ? "on disk" : "in host memory");
+    IcWriter w;
+    if (write_files &&
+        (rc = w.open(P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, ws, P.qdensity, P.qdensity ? density_path_of(P).c_str() : nullptr)))
+        return rc;
+    BlockStore st;
+    if ((rc = st.open(G, blk, disk, fs::path(P.output_dir)))) return rc;
+    // pass 1 (the reference's ZeldovichZ): the rows of rank s — generated, x and z transformed — go out as G blocks
+    for (int s = 0; s < G; s++) {
+        if ((rc = zplt_slab_set_rank(ctx, s))) return rc;
+        if ((rc = zplt_generate(ctx))) return rc;
+        if ((rc = zplt_synchronize(ctx))) return rc;
+        for (int d = 0; d < G; d++)
+            if ((rc = st.put(s, d, (const unsigned char *) send + (size_t) d * blk))) return rc;
+    }
+    // pass 2 (ZeldovichXY): the planes of rank d come back from every source, y transform + records
+    const int64_t nloc = P.ppd / G;
+    for (int d = 0; d < G; d++) {
+        if ((rc = zplt_slab_set_rank(ctx, d))) return rc;
+        for (int s = 0; s < G; s++)
+            if ((rc = st.get(s, d, (unsigned char *) recv + (size_t) s * blk))) return rc;
+        st.release(d);
+        if ((rc = zplt_exchange_adopt(ctx))) return rc;
+        if (write_files)
+            rc = w.write(ctx, d * nloc, nloc);
+        else
+            rc = drain_planes(ctx, P.ppd, cfg.icformat, nloc);
+        if (rc) return rc;
+    }
+    w.close();
+    rep->ooc_passes     = G;
+    rep->ooc_disk       = disk ? 1 : 0;
+    rep->ooc_bytes      = st.bytes;
+    rep->seconds_blocks = st.seconds;
+    st.close();
+    return ZPLT_OK;
+}
+
 // ---------------------------------------------------------------- whole run -------
 extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32_t write_files, zplt_run_report *rep) {
     if (!param_file) return hfail(ZPLT_EINVAL, "null argument");
@@ -439,9 +685,18 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
         zplt_power_destroy(pk);
         return rc;
     }
-    cfg.device    = device;
+    cfg.device = device;
+    int passes = 0;
+    if ((rc = choose_passes(P, cfg, device, &passes))) {
+        zplt_power_destroy(pk);
+        return rc;
+    }
+    if (passes) {
+        if (cfg.f_NL != 0.) rc = hfail(ZPLT_EINVAL, "ZD_f_NL does not run out of core");
+        cfg.rank = 0, cfg.nranks = passes;
+    }
     zplt_ctx *ctx = nullptr;
-    if ((rc = zplt_create(&cfg, &ctx))) {
+    if (rc || (rc = zplt_create(&cfg, &ctx))) {
         zplt_power_destroy(pk);
         return rc;
     }
@@ -458,27 +713,21 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
     fprintf(stderr, "Preamble took %f seconds\n", rep->seconds_preamble);
 
     const double t_dev = now_s();
-    if ((rc = zplt_generate(ctx))) return bail(rc);
     WriteStats ws;
-    if (write_files) {
-        if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, &ws, P.qdensity,
-                                 P.qdensity ? density_path_of(P).c_str() : nullptr)))
-            return bail(rc);
+    if (passes) {
+        if ((rc = run_out_of_core(ctx, P, cfg, passes, write_files, rep, &ws))) return bail(rc);
     } else {
-        // still run the emission (statistics) without keeping the records
-        const size_t plane = (size_t) P.ppd * P.ppd * zplt_record_bytes(cfg.icformat);
-        int64_t chunk      = (int64_t) ((512ull << 20) / plane);
-        if (chunk < 1) chunk = 1;
-        if (chunk > P.ppd) chunk = P.ppd;
-        HostBuffer buf((size_t) chunk * plane);
-        if (!buf.p) return bail(hfail(ZPLT_ENOMEM, "cannot allocate host staging"));
-        for (int64_t z0 = 0; z0 < P.ppd; z0 += chunk) {
-            int64_t nz = (z0 + chunk <= P.ppd) ? chunk : P.ppd - z0;
-            if ((rc = zplt_fetch_planes(ctx, z0, nz, buf.p))) return bail(rc);
+        if ((rc = zplt_generate(ctx))) return bail(rc);
+        if (write_files) {
+            if ((rc = write_ic_files(ctx, P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, &ws, P.qdensity,
+                                     P.qdensity ? density_path_of(P).c_str() : nullptr)))
+                return bail(rc);
+        } else if ((rc = drain_planes(ctx, P.ppd, cfg.icformat, P.ppd))) {  // still run the emission (statistics)
+            return bail(rc);
         }
     }
     if ((rc = zplt_synchronize(ctx))) return bail(rc);
-    rep->seconds_device = now_s() - t_dev - ws.seconds;
+    rep->seconds_device = now_s() - t_dev - ws.seconds - rep->seconds_blocks;
     rep->seconds_write  = ws.seconds;
     double tm[8];
     if ((rc = zplt_get_timings(ctx, tm))) return bail(rc);
@@ -501,6 +750,9 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
                 (int) (P.boxsize / (2 * fabs(rep->max_disp[2]))));
     }
     fprintf(stderr, "Device stages: generate %.3f ms, z-FFT %.3f ms, y-FFT %.3f ms, x-FFT+emit %.3f ms\n", tm[0], tm[1], tm[2], tm[3]);
+    if (passes)
+        fprintf(stderr, "Block IO took %.2f sec to move %.2f GB out and back ==> %.1f MB/sec\n", rep->seconds_blocks, 2 * rep->ooc_bytes / 1e9,
+                2 * rep->ooc_bytes / 1e6 / (rep->seconds_blocks > 0 ? rep->seconds_blocks : 1e-9));
     if (write_files)
         fprintf(stderr, "Writing ic files took %.3g sec to write %.3g MB ==> %.3g MB/sec\n", ws.seconds, ws.bytes / 1e6,
                 ws.bytes / 1e6 / (ws.seconds > 0 ? ws.seconds : 1e-9));
