@@ -587,6 +587,9 @@ def test_out_of_core_run_matches_oracle(pkg, oracle, monkeypatch, passes, store,
     again = oracle.read_ic_dir(out, N, cpd, kw["icformat"])
     compare_records(oracle, again, want)
     assert np.array_equal(again.view(np.uint8), got.view(np.uint8))  # same kernels, same arithmetic: not one bit differs
+    import shutil
+
+    shutil.rmtree(out, ignore_errors=True)
 
 
 @pytest.mark.parametrize("G,opts,case", [
