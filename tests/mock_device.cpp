@@ -148,6 +148,8 @@ extern "C" int zplt_copy_h2d_(void *dev, const void *host, size_t bytes) {
     memcpy(dev, host, bytes);
     return ZPLT_OK;
 }
+extern "C" int zplt_set_device_(int) { return ZPLT_OK; }
+extern "C" int zplt_ctx_device_(const zplt_ctx *) { return 0; }
 extern "C" int zplt_device_free_bytes_(int, size_t *free_b) {
     const char *e = getenv("ZPLT_MOCK_FREE_BYTES");
     *free_b       = e ? (size_t) strtoull(e, nullptr, 10) : (size_t) 180 << 30;

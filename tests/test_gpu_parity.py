@@ -556,6 +556,7 @@ def test_slab_decomposition_single_process(pkg, oracle, G, case):
     (2, "disk", dict(ppd=64, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVdoubleZel", eig=16)),
     (8, "ram", dict(ppd=128, qPLT=1, icformat="RVZel", eig=128)),
     (16, "disk", dict(ppd=256, k_cutoff=2.0, icformat="Zeldovich")),
+    (2, "pageable", dict(ppd=128, qPLT=1, qPLTrescale=1, PLT_target_z=5.0, icformat="RVZel", eig=128)),  # 32 MiB chunks, 2 copy threads
 ])
 def test_out_of_core_run_matches_oracle(pkg, oracle, monkeypatch, passes, store, case):
     """zplt_run_param_file out of core (the reference's -DDISK mode, src/block_array.cpp:129-382): one context plays the slab

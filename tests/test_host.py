@@ -302,8 +302,9 @@ def _check_mock_files(out, ppd, cpd, rb, planes=None):
             assert np.array_equal(data[i * words:(i + 1) * words], (np.uint32(z) << np.uint32(20)) ^ j), (k, z)
 
 
-@pytest.mark.parametrize("store", ["ram", "disk"])
-@pytest.mark.parametrize("passes,ppd,cpd,fmt,qplt", [(4, 32, 5, "RVZel", 0), (2, 16, 16, "RVdoubleZel", 1), (8, 32, 3, "ZelSimple", 0), (16, 32, 32, "Zeldovich", 0)])
+@pytest.mark.parametrize("store", ["ram", "pageable", "disk"])
+@pytest.mark.parametrize("passes,ppd,cpd,fmt,qplt", [(4, 32, 5, "RVZel", 0), (2, 16, 16, "RVdoubleZel", 1), (8, 32, 3, "ZelSimple", 0), (16, 32, 32, "Zeldovich", 0),
+                                                     (2, 128, 7, "RVZel", 1), (2, 256, 9, "ZelSimple", 0)])
 def test_out_of_core_pass_scheduling(mocklib, store, passes, ppd, cpd, fmt, qplt):
     """zplt_run_param_file out of core (reference -DDISK, src/block_array.cpp:129-382): block (s, d) must reach rank d's receive
     buffer at position s (the mock's zplt_exchange_adopt checks every value), planes must reach the ic files in ascending z,

@@ -1299,6 +1299,11 @@ extern "C" int zplt_copy_h2d_(void *dev, const void *host, size_t bytes) {
     CK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
     return ZPLT_OK;
 }
+extern "C" int zplt_set_device_(int device) {  // a host thread of the out-of-core block store joins the context's device
+    if (device >= 0) CK(cudaSetDevice(device));
+    return ZPLT_OK;
+}
+extern "C" int zplt_ctx_device_(const zplt_ctx *c) { return c ? c->device : -1; }
 extern "C" int zplt_device_free_bytes_(int device, size_t *free_b) {
     size_t total = 0;
     if (device >= 0) CK(cudaSetDevice(device));

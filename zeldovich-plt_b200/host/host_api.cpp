@@ -217,8 +217,8 @@ extern "C" void zplt_pinned_free_(void *p);
 struct HostBuffer {
     unsigned char *p = nullptr;
     bool pinned      = false;
-    explicit HostBuffer(size_t bytes) {
-        p = (unsigned char *) zplt_pinned_alloc_(bytes);
+    explicit HostBuffer(size_t bytes, bool pin = true) {
+        if (pin) p = (unsigned char *) zplt_pinned_alloc_(bytes);
         pinned = p != nullptr;
         if (!p) p = (unsigned char *) malloc(bytes);
     }
@@ -466,22 +466,71 @@ extern "C" int zplt_copy_d2h_(void *host, const void *dev, size_t bytes);
 extern "C" int zplt_copy_h2d_(void *dev, const void *host, size_t bytes);
 extern "C" int zplt_device_free_bytes_(int device, size_t *free_b);
 
+extern "C" int zplt_set_device_(int device);
+extern "C" int zplt_ctx_device_(const zplt_ctx *ctx);
+
+// Where the blocks wait between the passes.
+//   pinned   : page-locked host memory, one copy per block.  Simple, PCIe rate, but page-locking the whole cube costs ~0.5 s
+//              per GiB up front (measured: 33 of 44 s at PPD=1024).
+//   pageable : ordinary memory that is never page-locked; a few threads move every block in 32 MiB chunks through their own
+//              small pinned buffers (device <-> pinned by the copy engine, pinned <-> store by the thread), so the first touch of
+//              the store's pages is spread over the threads and overlaps the transfers.
+//   disk     : the reference's block files, through one pinned block buffer.
+enum StoreKind { STORE_PINNED = 0, STORE_PAGEABLE = 1, STORE_DISK = 2 };
+
 struct BlockStore {
+    static constexpr size_t CHUNK = 32u << 20;
     int G      = 0;
     size_t blk = 0;
     bool disk  = false;
+    int kind   = STORE_PINNED;
+    int device = -1;
     fs::path dir;
-    std::vector<std::unique_ptr<HostBuffer>> ram;  // [d]: blocks (0..G-1, d), released once rank d has emitted
-    std::unique_ptr<HostBuffer> bounce;             // disk: one block on its way to or from a file
+    std::vector<std::unique_ptr<HostBuffer>> ram;     // [d]: blocks (0..G-1, d), released once rank d has emitted
+    std::unique_ptr<HostBuffer> bounce;                // disk: one block on its way to or from a file
+    std::vector<std::unique_ptr<HostBuffer>> lanes;   // pageable: one pinned chunk buffer per copy thread
     double seconds = 0;
     int64_t bytes  = 0;
+
+    // one block between the device and the pageable store, chunk by chunk, every lane a thread
+    int move_chunks(unsigned char *host, unsigned char *dev, bool to_host) {
+        const size_t nchunks = (blk + CHUNK - 1) / CHUNK;
+        std::atomic<size_t> next{0};
+        std::atomic<int> rc{ZPLT_OK};
+        auto lane = [&](int i) {
+            if (zplt_set_device_(device) != ZPLT_OK) {
+                rc.store(ZPLT_ECUDA);
+                return;
+            }
+            unsigned char *b = lanes[i]->p;
+            for (;;) {
+                const size_t c = next.fetch_add(1);
+                if (c >= nchunks || rc.load() != ZPLT_OK) return;
+                const size_t off = c * CHUNK, n = std::min(CHUNK, blk - off);
+                int r;
+                if (to_host) {
+                    if ((r = zplt_copy_d2h_(b, dev + off, n)) == ZPLT_OK) memcpy(host + off, b, n);
+                } else {
+                    memcpy(b, host + off, n);
+                    r = zplt_copy_h2d_(dev + off, b, n);
+                }
+                if (r != ZPLT_OK) rc.store(r);
+            }
+        };
+        const int nt = (int) std::min<size_t>(lanes.size(), nchunks);
+        std::vector<std::thread> pool;
+        for (int i = 1; i < nt; i++) pool.emplace_back(lane, i);
+        lane(0);
+        for (auto &t : pool) t.join();
+        return rc.load();
+    }
 
     ~BlockStore() { close(); }
     fs::path block_dir(int s) const { return dir / ("zeldovich." + std::to_string(s)); }
     fs::path block_file(int s, int d) const { return block_dir(s) / ("zeldovich." + std::to_string(s) + "." + std::to_string(d)); }
 
-    int open(int G_, size_t blk_, bool disk_, const fs::path &dir_) {
-        G = G_, blk = blk_, disk = disk_, dir = dir_;
+    int open(int G_, size_t blk_, int kind_, const fs::path &dir_, int device_) {
+        G = G_, blk = blk_, kind = kind_, disk = kind_ == STORE_DISK, dir = dir_, device = device_;
         if (disk) {
             std::error_code ec;
             for (int s = 0; s < G; s++) {
@@ -493,8 +542,16 @@ struct BlockStore {
         } else {
             ram.resize(G);
             for (int d = 0; d < G; d++) {
-                ram[d].reset(new HostBuffer((size_t) G * blk));
+                ram[d].reset(new HostBuffer((size_t) G * blk, kind == STORE_PINNED));
                 if (!ram[d]->p) return hfail(ZPLT_ENOMEM, "cannot allocate %zu bytes of host memory for the blocks of pass %d", (size_t) G * blk, d);
+            }
+            if (kind == STORE_PAGEABLE) {
+                int nt = (int) std::thread::hardware_concurrency();
+                nt     = std::max(1, std::min(nt, 8));
+                for (int i = 0; i < nt; i++) {
+                    lanes.emplace_back(new HostBuffer(CHUNK));
+                    if (!lanes.back()->p) return hfail(ZPLT_ENOMEM, "cannot allocate the copy threads' buffers");
+                }
             }
         }
         return ZPLT_OK;
@@ -502,7 +559,9 @@ struct BlockStore {
     int put(int s, int d, const void *dev) {
         const double t0 = now_s();
         int rc;
-        if (!disk) {
+        if (kind == STORE_PAGEABLE) {
+            rc = move_chunks(ram[d]->p + (size_t) s * blk, (unsigned char *) const_cast<void *>(dev), true);
+        } else if (!disk) {
             rc = zplt_copy_d2h_(ram[d]->p + (size_t) s * blk, dev, blk);
         } else if ((rc = zplt_copy_d2h_(bounce->p, dev, blk)) == ZPLT_OK) {
             FILE *fp  = fopen(block_file(s, d).c_str(), "wb");
@@ -517,7 +576,9 @@ struct BlockStore {
     int get(int s, int d, void *dev) {
         const double t0 = now_s();
         int rc;
-        if (!disk) {
+        if (kind == STORE_PAGEABLE) {
+            rc = move_chunks(ram[d]->p + (size_t) s * blk, (unsigned char *) dev, false);
+        } else if (!disk) {
             rc = zplt_copy_h2d_(dev, ram[d]->p + (size_t) s * blk, blk);
         } else {
             FILE *fp  = fopen(block_file(s, d).c_str(), "rb");
@@ -543,6 +604,7 @@ struct BlockStore {
             }
         }
         bounce.reset();
+        lanes.clear();
         G = 0;
     }
 };
@@ -618,24 +680,27 @@ static int run_out_of_core(zplt_ctx *ctx, const zplt_params &P, const zplt_confi
     int rc     = zplt_exchange_info(ctx, &send, &recv, &blk);
     if (rc) return rc;
     const int64_t cube_bytes = (int64_t) G * G * (int64_t) blk;
-    bool disk                = false;
+    int kind                 = STORE_PINNED;
     if (const char *e = getenv("ZPLT_OOC_STORE")) {
         if (strcmp(e, "disk") == 0)
-            disk = true;
+            kind = STORE_DISK;
+        else if (strcmp(e, "pageable") == 0)
+            kind = STORE_PAGEABLE;
         else if (strcmp(e, "ram") != 0)
-            return hfail(ZPLT_EINVAL, "ZPLT_OOC_STORE must be \"ram\" or \"disk\"");
+            return hfail(ZPLT_EINVAL, "ZPLT_OOC_STORE must be \"ram\", \"pageable\" or \"disk\"");
     } else {
         const int64_t avail = host_mem_available();
-        disk                = avail > 0 && cube_bytes + (cube_bytes >> 4) + (8ll << 30) > avail;
+        if (avail > 0 && cube_bytes + (cube_bytes >> 4) + (8ll << 30) > avail) kind = STORE_DISK;
     }
+    const bool disk = kind == STORE_DISK;
     fprintf(stderr, "Out of core: %d passes over %.3f GiB, blocks of %.3f GiB buffered %s\n", G, cube_bytes / 1073741824.0,
-            blk / 1073741824.0, disk ? "on disk" : "in host memory");
+            blk / 1073741824.0, disk ? "on disk" : (kind == STORE_PAGEABLE ? "in pageable host memory" : "in pinned host memory"));
     IcWriter w;
     if (write_files &&
         (rc = w.open(P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, ws, P.qdensity, P.qdensity ? density_path_of(P).c_str() : nullptr)))
         return rc;
     BlockStore st;
-    if ((rc = st.open(G, blk, disk, fs::path(P.output_dir)))) return rc;
+    if ((rc = st.open(G, blk, kind, fs::path(P.output_dir), zplt_ctx_device_(ctx)))) return rc;
     // pass 1 (the reference's ZeldovichZ): the rows of rank s — generated, x and z transformed — go out as G blocks
     for (int s = 0; s < G; s++) {
         if ((rc = zplt_slab_set_rank(ctx, s))) return rc;
