@@ -305,7 +305,8 @@ typedef struct zplt_run_report {
 /* The cube is kept in HBM when it fits.  Otherwise — or when the environment variable ZPLT_OOC_PASSES=G forces it — the run
  * goes out of core in G passes (see zplt_slab_set_rank), the blocks parked in host memory, or in files
  * `zeldovich.{s}/zeldovich.{s}.{d}` under InitialConditionsDirectory (the reference's names, src/block_array.cpp:136) when
- * host memory is too small or ZPLT_OOC_STORE=disk. */
+ * host memory is too small or ZPLT_OOC_STORE=disk.  ZPLT_OOC_STORE=ram is the default page-locked store, =pageable ordinary
+ * memory filled by several copy threads through small page-locked buffers (no up-front page-locking of the whole cube). */
 int zplt_run_param_file(const char *param_file, int32_t device, int32_t write_files, zplt_run_report *report);
 
 #ifdef __cplusplus
