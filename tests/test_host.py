@@ -302,14 +302,20 @@ def _check_mock_files(out, ppd, cpd, rb, planes=None):
             assert np.array_equal(data[i * words:(i + 1) * words], (np.uint32(z) << np.uint32(20)) ^ j), (k, z)
 
 
+@pytest.mark.parametrize("chunk_planes", [0, 3])
 @pytest.mark.parametrize("store", ["ram", "pageable", "disk"])
 @pytest.mark.parametrize("passes,ppd,cpd,fmt,qplt", [(4, 32, 5, "RVZel", 0), (2, 16, 16, "RVdoubleZel", 1), (8, 32, 3, "ZelSimple", 0), (16, 32, 32, "Zeldovich", 0),
                                                      (2, 128, 7, "RVZel", 1), (2, 256, 9, "ZelSimple", 0)])
-def test_out_of_core_pass_scheduling(mocklib, store, passes, ppd, cpd, fmt, qplt):
+def test_out_of_core_pass_scheduling(mocklib, monkeypatch, store, passes, ppd, cpd, fmt, qplt, chunk_planes):
     """zplt_run_param_file out of core (reference -DDISK, src/block_array.cpp:129-382): block (s, d) must reach rank d's receive
     buffer at position s (the mock's zplt_exchange_adopt checks every value), planes must reach the ic files in ascending z,
     block files carry the reference's names while they exist and are gone afterwards."""
     synth = load_synth()
+    rb = {"RVZel": 32, "RVdoubleZel": 56, "ZelSimple": 12, "Zeldovich": 32}[fmt]
+    if chunk_planes:
+        if ppd > 128:
+            pytest.skip("small-chunk variant only for the small grids")
+        monkeypatch.setenv("ZPLT_IC_CHUNK_BYTES", str(chunk_planes * ppd * ppd * rb))  # chunks that straddle pass boundaries or not
     with tempfile.TemporaryDirectory() as tmp:
         over = dict(NP=ppd**3, CPD=cpd, ICFormat='"%s"' % fmt)
         if qplt:
@@ -317,7 +323,6 @@ def test_out_of_core_pass_scheduling(mocklib, store, passes, ppd, cpd, fmt, qplt
             over.update(ZD_qPLT=1, ZD_PLT_filename='"%s"' % os.path.join(tmp, "eig"))
         rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": str(passes), "ZPLT_OOC_STORE": store}, **over)
         assert rc == 0, err
-        rb = {"RVZel": 32, "RVdoubleZel": 56, "ZelSimple": 12, "Zeldovich": 32}[fmt]
         _check_mock_files(out, ppd, cpd, rb)
         assert rep.ooc_passes == passes and rep.ooc_disk == (store == "disk")
         assert rep.ooc_bytes == 16 * (4 if qplt else 2) * ppd**3  # the whole cube went out once
@@ -358,3 +363,50 @@ def test_out_of_core_options_and_auto_passes(mocklib):
         assert rc != 0 and "16 passes" in err
         rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": "2", "ZPLT_OOC_STORE": "tape"}, NP=ppd**3, CPD=4)
         assert rc != 0 and "ZPLT_OOC_STORE" in err
+
+
+@pytest.mark.parametrize("ppd,cpd,fmt,chunk_planes", [(32, 5, "RVZel", 0), (256, 256, "ZelSimple", 0), (64, 7, "RVZel", 5), (32, 32, "RVZel", 1)])
+def test_ic_writer_resident_options(mocklib, monkeypatch, ppd, cpd, fmt, chunk_planes):
+    """zplt_write_outputs on a resident context (mock device half): ZD_qdensity 0/1/2 and ZD_qoneslab, the writer's chunking
+    (ppd=256 ZelSimple is 201 MB of records in one chunk of planes; ppd=32 shares files between planes), stale files removed."""
+    import ctypes as C
+
+    L, pkg = mocklib
+    rb = {"RVZel": 32, "ZelSimple": 12}[fmt]
+    if chunk_planes:  # many chunks: both staging buffers in use, writers overlapped with the next fetch
+        monkeypatch.setenv("ZPLT_IC_CHUNK_BYTES", str(chunk_planes * ppd * ppd * rb))
+    cfg = pkg.make_config(ppd, icformat=fmt)
+    ctx = C.c_void_p()
+    assert L.zplt_create(C.byref(cfg), C.byref(ctx)) == 0
+    L.zplt_set_power_law.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.zplt_write_outputs.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    assert L.zplt_set_power_law(ctx, 1.0, 1.0, 0.0) == 0
+    L.zplt_generate.argtypes = [C.c_void_p]
+    assert L.zplt_generate(ctx) == 0
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "ic")
+        dens = os.path.join(tmp, "density")
+        os.makedirs(out)
+        open(os.path.join(out, "ic_9999"), "w").write("stale")
+        open(os.path.join(out, "zeldovich.0.0"), "w").write("stale")
+        open(os.path.join(out, "keep.txt"), "w").write("not ours")
+        assert L.zplt_write_outputs(ctx, os.fsencode(out), cpd, 0, None, -1) == 0, L.zplt_last_error()
+        assert os.path.exists(os.path.join(out, "keep.txt")) and not os.path.exists(os.path.join(out, "zeldovich.0.0"))
+        os.remove(os.path.join(out, "keep.txt"))
+        _check_mock_files(out, ppd, cpd, rb)
+        # records + density
+        assert L.zplt_write_outputs(ctx, os.fsencode(out), cpd, 1, os.fsencode(dens), -1) == 0, L.zplt_last_error()
+        _check_mock_files(out, ppd, cpd, rb)
+        d = np.fromfile(dens, dtype=np.float32).reshape(ppd, ppd * ppd)
+        assert np.array_equal(d[:, 0], np.arange(ppd, dtype=np.float32)) and np.all(d == d[:, :1])
+        # density only: no ic files at all
+        assert L.zplt_write_outputs(ctx, os.fsencode(out), cpd, 2, os.fsencode(dens), -1) == 0, L.zplt_last_error()
+        assert not [f for f in os.listdir(out) if f.startswith("ic_")]
+        assert os.path.getsize(dens) == 4 * ppd**3
+        # one plane; a plane number beyond the grid writes nothing (the reference's loop never matches)
+        assert L.zplt_write_outputs(ctx, os.fsencode(out), cpd, 0, None, ppd - 3) == 0, L.zplt_last_error()
+        _check_mock_files(out, ppd, cpd, rb, planes=[ppd - 3])
+        assert L.zplt_write_outputs(ctx, os.fsencode(out), cpd, 0, None, ppd + 5) == 0, L.zplt_last_error()
+        assert not [f for f in os.listdir(out) if f.startswith("ic_")]
+    L.zplt_destroy.argtypes = [C.c_void_p]
+    L.zplt_destroy(ctx)

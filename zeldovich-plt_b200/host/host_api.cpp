@@ -304,7 +304,9 @@ struct IcWriter {
 
         plane  = (size_t) ppd * ppd * zplt_record_bytes(icformat);
         dplane = (size_t) ppd * ppd * sizeof(float);
-        chunk  = (int64_t) ((1024ull << 20) / plane);
+        size_t chunk_bytes = 1024ull << 20;
+        if (const char *e = getenv("ZPLT_IC_CHUNK_BYTES")) chunk_bytes = (size_t) strtoull(e, nullptr, 10);  // tests: small chunks
+        chunk = (int64_t) (chunk_bytes / plane);
         if (chunk < 1) chunk = 1;
         if (chunk > ppd) chunk = ppd;
         records = qdensity != 2;
