@@ -12,7 +12,7 @@
 
 #include "../include/zeldovich_b200.h"
 
-static std::string g_err;
+static thread_local std::string g_err;  // per thread, as in the device half
 extern "C" void zplt_set_error_(const char *msg) { g_err = msg ? msg : ""; }
 extern "C" const char *zplt_last_error(void) { return g_err.c_str(); }
 static int fail(int code, const char *msg) {
@@ -140,11 +140,21 @@ extern "C" int zplt_ctx_ppd_(const zplt_ctx *c) { return c->N; }
 extern "C" int zplt_ctx_icformat_(const zplt_ctx *c) { return c->cfg.icformat; }
 extern "C" void *zplt_pinned_alloc_(size_t bytes) { return malloc(bytes); }
 extern "C" void zplt_pinned_free_(void *p) { free(p); }
+// ZPLT_MOCK_FAIL_COPY=n: the n-th copy of the process (counted from 1, either direction) fails like a CUDA error would
+#include <atomic>
+static std::atomic<long> g_copies{0};
+static bool copy_fails() {
+    const char *e = getenv("ZPLT_MOCK_FAIL_COPY");
+    return e && ++g_copies == atol(e);
+}
+extern "C" void zplt_mock_reset_copies(void) { g_copies = 0; }
 extern "C" int zplt_copy_d2h_(void *host, const void *dev, size_t bytes) {
+    if (copy_fails()) return fail(ZPLT_ECUDA, "mock: cudaMemcpy device to host failed");
     memcpy(host, dev, bytes);
     return ZPLT_OK;
 }
 extern "C" int zplt_copy_h2d_(void *dev, const void *host, size_t bytes) {
+    if (copy_fails()) return fail(ZPLT_ECUDA, "mock: cudaMemcpy host to device failed");
     memcpy(dev, host, bytes);
     return ZPLT_OK;
 }

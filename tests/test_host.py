@@ -272,7 +272,8 @@ def _mock_run(mocklib, tmp, env, write_files=1, **over):
     out = os.path.join(tmp, "ic")
     par = write_case(tmp, InitialConditionsDirectory='"%s"' % out, **over)
     rep = pkg.RunReport()
-    keys = ("ZPLT_OOC_PASSES", "ZPLT_OOC_STORE", "ZPLT_MOCK_FREE_BYTES")
+    keys = ("ZPLT_OOC_PASSES", "ZPLT_OOC_STORE", "ZPLT_MOCK_FREE_BYTES", "ZPLT_MOCK_FAIL_COPY")
+    L.zplt_mock_reset_copies()
     saved = {k: os.environ.pop(k, None) for k in keys}
     os.environ.update(env)
     try:
@@ -409,3 +410,14 @@ def test_ic_writer_resident_options(mocklib, monkeypatch, ppd, cpd, fmt, chunk_p
         assert not [f for f in os.listdir(out) if f.startswith("ic_")]
     L.zplt_destroy.argtypes = [C.c_void_p]
     L.zplt_destroy(ctx)
+
+
+@pytest.mark.parametrize("store,nth", [("ram", 3), ("ram", 20), ("pageable", 2), ("pageable", 9), ("disk", 5), ("disk", 21)])
+def test_out_of_core_copy_failure_is_reported(mocklib, store, nth):
+    """A failing block copy (either pass, any store, also inside a copy thread of the pageable store) ends the run with the
+    device half's message in the caller's thread, and leaves no block files behind."""
+    with tempfile.TemporaryDirectory() as tmp:
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": "4", "ZPLT_OOC_STORE": store, "ZPLT_MOCK_FAIL_COPY": str(nth)},
+                                      NP=32**3, CPD=4)
+        assert rc == 2 and "mock: cudaMemcpy" in err, (rc, err)  # ZPLT_ECUDA
+        assert not [f for f in os.listdir(out) if f.startswith("zeldovich.")]

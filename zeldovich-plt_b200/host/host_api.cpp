@@ -499,9 +499,15 @@ struct BlockStore {
         const size_t nchunks = (blk + CHUNK - 1) / CHUNK;
         std::atomic<size_t> next{0};
         std::atomic<int> rc{ZPLT_OK};
+        std::mutex emu;
+        std::string emsg;  // the error text is per thread (zplt_last_error): carry a lane's message back to the caller's thread
+        auto failed = [&](int code) {
+            std::lock_guard<std::mutex> g(emu);
+            if (rc.exchange(code) == ZPLT_OK) emsg = zplt_last_error();
+        };
         auto lane = [&](int i) {
-            if (zplt_set_device_(device) != ZPLT_OK) {
-                rc.store(ZPLT_ECUDA);
+            if (int r = zplt_set_device_(device)) {
+                failed(r);
                 return;
             }
             unsigned char *b = lanes[i]->p;
@@ -516,7 +522,7 @@ struct BlockStore {
                     memcpy(b, host + off, n);
                     r = zplt_copy_h2d_(dev + off, b, n);
                 }
-                if (r != ZPLT_OK) rc.store(r);
+                if (r != ZPLT_OK) failed(r);
             }
         };
         const int nt = (int) std::min<size_t>(lanes.size(), nchunks);
@@ -524,7 +530,7 @@ struct BlockStore {
         for (int i = 1; i < nt; i++) pool.emplace_back(lane, i);
         lane(0);
         for (auto &t : pool) t.join();
-        return rc.load();
+        return rc.load() == ZPLT_OK ? ZPLT_OK : hfail(rc.load(), "%s", emsg.c_str());
     }
 
     ~BlockStore() { close(); }
