@@ -299,13 +299,15 @@ typedef struct zplt_run_report {
     int64_t ppd, files_written, bytes_written;
     /* out-of-core runs: passes over the cube (0 = the cube was resident), 1 if the blocks went through files under
      * InitialConditionsDirectory instead of host memory, bytes parked, seconds spent copying/writing/reading them */
-    int64_t ooc_passes, ooc_disk, ooc_bytes;
+    int64_t ooc_passes, ooc_disk, ooc_bytes, ooc_part;
     double seconds_blocks;
 } zplt_run_report;
 /* The cube is kept in HBM when it fits.  Otherwise — or when the environment variable ZPLT_OOC_PASSES=G forces it — the run
  * goes out of core in G passes (see zplt_slab_set_rank), the blocks parked in host memory, or in files
  * `zeldovich.{s}/zeldovich.{s}.{d}` under InitialConditionsDirectory (the reference's names, src/block_array.cpp:136) when
- * host memory is too small or ZPLT_OOC_STORE=disk.  ZPLT_OOC_STORE=ram is the default page-locked store, =pageable ordinary
+ * host memory is too small or ZPLT_OOC_STORE=disk.  With block files the two passes can be two invocations, as with the
+ * reference's -DPART1 / -DPART2 builds: ZPLT_OOC_PART=1 stops after pass 1 and leaves the block files, ZPLT_OOC_PART=2 (same
+ * parameter file, same ZPLT_OOC_PASSES) reads them and writes the ic files.  ZPLT_OOC_STORE=ram is the default page-locked store, =pageable ordinary
  * memory filled by several copy threads through small page-locked buffers (no up-front page-locking of the whole cube). */
 int zplt_run_param_file(const char *param_file, int32_t device, int32_t write_files, zplt_run_report *report);
 

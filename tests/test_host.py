@@ -272,7 +272,7 @@ def _mock_run(mocklib, tmp, env, write_files=1, **over):
     out = os.path.join(tmp, "ic")
     par = write_case(tmp, InitialConditionsDirectory='"%s"' % out, **over)
     rep = pkg.RunReport()
-    keys = ("ZPLT_OOC_PASSES", "ZPLT_OOC_STORE", "ZPLT_MOCK_FREE_BYTES", "ZPLT_MOCK_FAIL_COPY")
+    keys = ("ZPLT_OOC_PASSES", "ZPLT_OOC_STORE", "ZPLT_MOCK_FREE_BYTES", "ZPLT_MOCK_FAIL_COPY", "ZPLT_OOC_PART")
     L.zplt_mock_reset_copies()
     saved = {k: os.environ.pop(k, None) for k in keys}
     os.environ.update(env)
@@ -421,3 +421,27 @@ def test_out_of_core_copy_failure_is_reported(mocklib, store, nth):
                                       NP=32**3, CPD=4)
         assert rc == 2 and "mock: cudaMemcpy" in err, (rc, err)  # ZPLT_ECUDA
         assert not [f for f in os.listdir(out) if f.startswith("zeldovich.")]
+
+
+def test_out_of_core_in_two_invocations(mocklib):
+    """ZPLT_OOC_PART=1 then =2 (the reference's -DPART1 / -DPART2 builds, src/zeldovich.cpp:938-979): the first run leaves
+    passes^2 block files with the reference's names and no ic files, the second turns them into the ic files and removes them."""
+    ppd, cpd, G = 32, 5, 4
+    with tempfile.TemporaryDirectory() as tmp:
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": str(G), "ZPLT_OOC_PART": "1"}, NP=ppd**3, CPD=cpd)
+        assert rc == 0 and rep.ooc_part == 1 and rep.ooc_disk == 1, err
+        blk = 16 * 2 * ppd**3 // G**2
+        for s in range(G):
+            assert sorted(os.listdir(os.path.join(out, f"zeldovich.{s}"))) == [f"zeldovich.{s}.{d}" for d in range(G)]
+            assert all(os.path.getsize(os.path.join(out, f"zeldovich.{s}", f"zeldovich.{s}.{d}")) == blk for d in range(G))
+        assert not [f for f in os.listdir(out) if f.startswith("ic_")] and rep.density_variance == 0
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": str(G), "ZPLT_OOC_PART": "2"}, NP=ppd**3, CPD=cpd)
+        assert rc == 0 and rep.ooc_part == 2, err
+        _check_mock_files(out, ppd, cpd, 32)  # the mock checks every value of every block it adopts
+        assert rep.density_variance == ppd and rep.max_disp[0] == 0  # every plane emitted, nothing generated in this invocation
+        assert not [f for f in os.listdir(out) if f.startswith("zeldovich.")]
+        # pass 2 without the blocks of a pass 1, and the split without an explicit blocking, are errors
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PASSES": str(G), "ZPLT_OOC_PART": "2"}, NP=ppd**3, CPD=cpd)
+        assert rc != 0 and "cannot read block file" in err
+        rc, rep, out, err = _mock_run(mocklib, tmp, {"ZPLT_OOC_PART": "1", "ZPLT_MOCK_FREE_BYTES": str((1 << 30) + 16 * 2 * ppd**3 - 1)}, NP=ppd**3, CPD=cpd)
+        assert rc != 0 and "ZPLT_OOC_PASSES" in err

@@ -84,7 +84,7 @@ class RunReport(C.Structure):
         ("seconds_total", C.c_double), ("seconds_preamble", C.c_double), ("seconds_device", C.c_double),
         ("seconds_write", C.c_double), ("stage_ms", C.c_double * 4),
         ("ppd", C.c_int64), ("files_written", C.c_int64), ("bytes_written", C.c_int64),
-        ("ooc_passes", C.c_int64), ("ooc_disk", C.c_int64), ("ooc_bytes", C.c_int64), ("seconds_blocks", C.c_double),
+        ("ooc_passes", C.c_int64), ("ooc_disk", C.c_int64), ("ooc_bytes", C.c_int64), ("ooc_part", C.c_int64), ("seconds_blocks", C.c_double),
     ]
 
 

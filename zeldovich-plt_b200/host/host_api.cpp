@@ -493,6 +493,7 @@ struct BlockStore {
     std::vector<std::unique_ptr<HostBuffer>> lanes;   // pageable: one pinned chunk buffer per copy thread
     double seconds = 0;
     int64_t bytes  = 0;
+    bool keep      = false;  // leave the block files where they are (pass 1 of a run split over two invocations)
 
     // one block between the device and the pageable store, chunk by chunk, every lane a thread
     int move_chunks(unsigned char *host, unsigned char *dev, bool to_host) {
@@ -604,7 +605,7 @@ struct BlockStore {
     }
     void close() {
         ram.clear();
-        if (disk) {
+        if (disk && !keep) {
             std::error_code ec;
             for (int s = 0; s < G; s++) {
                 for (int d = 0; d < G; d++) fs::remove(block_file(s, d), ec);
@@ -700,17 +701,27 @@ static int run_out_of_core(zplt_ctx *ctx, const zplt_params &P, const zplt_confi
         const int64_t avail = host_mem_available();
         if (avail > 0 && cube_bytes + (cube_bytes >> 4) + (8ll << 30) > avail) kind = STORE_DISK;
     }
+    // ZPLT_OOC_PART=1: pass 1 only, the block files stay; ZPLT_OOC_PART=2: pass 2 only, from the block files of an earlier
+    // invocation with the same parameter file and pass count (the reference's -DPART1 / -DPART2 builds, src/zeldovich.cpp:938-979)
+    int part = 0;
+    if (const char *e = getenv("ZPLT_OOC_PART")) {
+        part = atoi(e);
+        if (part < 0 || part > 2) return hfail(ZPLT_EINVAL, "ZPLT_OOC_PART must be 0, 1 or 2");
+        if (part && !getenv("ZPLT_OOC_PASSES")) return hfail(ZPLT_EINVAL, "ZPLT_OOC_PART needs ZPLT_OOC_PASSES (both invocations must use the same blocking)");
+        if (part) kind = STORE_DISK;
+    }
     const bool disk = kind == STORE_DISK;
     fprintf(stderr, "Out of core: %d passes over %.3f GiB, blocks of %.3f GiB buffered %s\n", G, cube_bytes / 1073741824.0,
             blk / 1073741824.0, disk ? "on disk" : (kind == STORE_PAGEABLE ? "in pageable host memory" : "in pinned host memory"));
     IcWriter w;
-    if (write_files &&
+    if (write_files && part != 1 &&
         (rc = w.open(P.ppd, cfg.icformat, P.output_dir, P.cpd, P.qoneslab, ws, P.qdensity, P.qdensity ? density_path_of(P).c_str() : nullptr)))
         return rc;
     BlockStore st;
     if ((rc = st.open(G, blk, kind, fs::path(P.output_dir), zplt_ctx_device_(ctx)))) return rc;
+    st.keep = part == 1;
     // pass 1 (the reference's ZeldovichZ): the rows of rank s — generated, x and z transformed — go out as G blocks
-    for (int s = 0; s < G; s++) {
+    for (int s = 0; s < G && part != 2; s++) {
         if ((rc = zplt_slab_set_rank(ctx, s))) return rc;
         if ((rc = zplt_generate(ctx))) return rc;
         if ((rc = zplt_synchronize(ctx))) return rc;
@@ -719,7 +730,7 @@ static int run_out_of_core(zplt_ctx *ctx, const zplt_params &P, const zplt_confi
     }
     // pass 2 (ZeldovichXY): the planes of rank d come back from every source, y transform + records
     const int64_t nloc = P.ppd / G;
-    for (int d = 0; d < G; d++) {
+    for (int d = 0; d < G && part != 1; d++) {
         if ((rc = zplt_slab_set_rank(ctx, d))) return rc;
         for (int s = 0; s < G; s++)
             if ((rc = st.get(s, d, (unsigned char *) recv + (size_t) s * blk))) return rc;
@@ -733,6 +744,7 @@ static int run_out_of_core(zplt_ctx *ctx, const zplt_params &P, const zplt_confi
     }
     w.close();
     rep->ooc_passes     = G;
+    rep->ooc_part       = part;
     rep->ooc_disk       = disk ? 1 : 0;
     rep->ooc_bytes      = st.bytes;
     rep->seconds_blocks = st.seconds;
@@ -802,13 +814,21 @@ extern "C" int zplt_run_param_file(const char *param_file, int32_t device, int32
     if ((rc = zplt_synchronize(ctx))) return bail(rc);
     rep->seconds_device = now_s() - t_dev - ws.seconds - rep->seconds_blocks;
     rep->seconds_write  = ws.seconds;
-    double tm[8];
-    if ((rc = zplt_get_timings(ctx, tm))) return bail(rc);
+    double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // (pass 2 of a split run never generated in this process: its context has no stage times to read)
+    if (rep->ooc_part != 2 && (rc = zplt_get_timings(ctx, tm))) return bail(rc);
     for (int i = 0; i < 4; i++) rep->stage_ms[i] = tm[i];
     if ((rc = zplt_get_stats(ctx, &rep->density_variance, rep->max_disp))) return bail(rc);
     rep->ppd           = P.ppd;
     rep->files_written = ws.files;
     rep->bytes_written = ws.bytes;
+    if (rep->ooc_part == 1) {  // nothing emitted yet: no statistics to print (the reference's -DNOPART2 build ends here too)
+        fprintf(stderr, "Wrote %d block files (%.2f GB in %.2f sec); run again with ZPLT_OOC_PART=2 for the ic files\n", passes * passes,
+                rep->ooc_bytes / 1e9, rep->seconds_blocks);
+        rep->seconds_total = now_s() - t_start;
+        bail(0);
+        return ZPLT_OK;
+    }
     rep->rms_density   = sqrt(rep->density_variance / ((double) P.ppd * P.ppd * P.ppd));
     rep->input_sigma   = 0;
     // the stderr summary of reference src/zeldovich.cpp:987-1011
